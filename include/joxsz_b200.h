@@ -1,0 +1,211 @@
+/* joxsz_b200.h -- C ABI of libjoxsz_b200.so: the batched JoXSZ joint SZ + X-ray log-likelihood
+ * on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for ONE path of fcastagna/JoXSZ: the per-walker likelihood that
+ * emcee calls once per walker per step (reference joxsz_funcs.py:507-546 `getLikelihood`, bound onto
+ * mbproj2's Fit at joxsz_main.py:186-188 and handed to emcee at joxsz_main.py:206).  The reference has
+ * no FFI of its own (it is pure Python); the Python binding a maintainer adds is a ctypes stub, shown
+ * in INTEGRATION.md.  Everything below takes plain pointers and sizes; no torch / CUDA types appear.
+ *
+ * Conventions
+ *   - every `double*` / `int32_t*` argument of a compute call is a DEVICE pointer on the handle's
+ *     device unless marked [host]; arrays are C order (row-major), float64;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous on it;
+ *   - every function returns 0 on success or a negative jx_status; nothing throws; the message of
+ *     the last failure is available from jx_last_error();
+ *   - a handle is not thread-safe; one handle per (device, stream);
+ *   - the library never allocates per call: workspace is sized at jx_create for `max_walkers`;
+ *   - there is no CPU fallback: jx_create fails if no sm_100-class device is present.
+ */
+#ifndef JOXSZ_B200_H
+#define JOXSZ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JX_ABI_VERSION 3
+
+typedef enum jx_status {
+    JX_OK = 0,
+    JX_ERR_INVALID = -1,   /* bad argument / unsupported geometry */
+    JX_ERR_CUDA = -2,      /* CUDA runtime error (see jx_last_error) */
+    JX_ERR_NO_DEVICE = -3, /* no usable sm_100 device */
+    JX_ERR_CAPACITY = -4   /* W exceeds max_walkers */
+} jx_status;
+
+/* Slots of the full physical parameter vector (names are the keys of the reference's `fit.pars`;
+ * defaults/bounds: joxsz_funcs.py:266-272, 318, 358-372; joxsz_main.py:131,156-157). */
+enum jx_param_slot {
+    JX_P0 = 0,      /* "P_0"              gNFW normalisation, keV cm^-3 */
+    JX_A,           /* "a"                                                 */
+    JX_B,           /* "b"                                                 */
+    JX_C,           /* "c"                                                 */
+    JX_RP,          /* "r_p"              kpc                              */
+    JX_LOGN0,       /* "log(n_0)"         log10 cm^-3                      */
+    JX_BETA,        /* "\\beta"                                            */
+    JX_LOGRC,       /* "log(r_c)"         log10 kpc                        */
+    JX_LOGRS,       /* "log(r_s)"         log10 kpc                        */
+    JX_ALPHA,       /* "\\alpha"                                           */
+    JX_EPS,         /* "\\epsilon"                                         */
+    JX_GAMMA,       /* "\\gamma"                                           */
+    JX_LOGN02,      /* "log(n_{02})"      (density mode 'double' only)     */
+    JX_BETA2,       /* "\\beta_2"                                          */
+    JX_LOGRC2,      /* "log(r_{c2})"                                       */
+    JX_LOGTRATIO,   /* "log(T_X/T_{SZ})"                                   */
+    JX_ZMET,        /* "Z"                solar                            */
+    JX_BACKSCALE,   /* "backscale"                                         */
+    JX_CALIB,       /* "calibration"                                       */
+    JX_NPAR
+};
+
+/* Per-walker status bits (jx_profiles `flags`): any bit set => log-likelihood is -inf. */
+#define JX_FLAG_PRIOR   1u /* a parameter prior is -inf or not finite   (joxsz_funcs.py:518-520) */
+#define JX_FLAG_MASS    2u /* hydrostatic mass not monotone             (joxsz_funcs.py:522-525) */
+#define JX_FLAG_RCRS    4u /* r_c > r_s                                 (joxsz_funcs.py:397-407, 536) */
+#define JX_FLAG_XNONPOS 8u /* an X-ray predicted profile is not > 0     (joxsz_funcs.py:529-532) */
+
+/* Everything jx_create needs, as [host] pointers; the library copies what it keeps.
+ * The Python side fills this from a built `fit` object (joxsz_b200/packer.py). */
+typedef struct jx_setup {
+    int32_t abi_version;             /* must be JX_ABI_VERSION */
+    int32_t device;                  /* CUDA device ordinal */
+    int32_t max_walkers;             /* workspace capacity */
+
+    /* -- parameters: theta[W, ndim] -> full vector (replaces Fit.updateThawed, joxsz_funcs.py:516) */
+    int32_t ndim;                    /* number of thawed (sampled) parameters */
+    int32_t slot_src[JX_NPAR];       /* >= 0: column of theta feeding this slot; -1: frozen */
+    double  slot_val[JX_NPAR];       /* value used when frozen */
+    int32_t dens_mode;               /* 0 = 'single', 1 = 'double' (joxsz_funcs.py:390-394) */
+    int32_t exclude_unphy_mass;      /* joxsz_main.py:88 */
+    /* priors, one per theta column (mbproj2 Param / ParamGaussian .prior()) */
+    const int32_t* prior_kind;       /* [ndim] 0 = box, 1 = Gaussian */
+    const double*  prior_a;          /* [ndim] minval | mu */
+    const double*  prior_b;          /* [ndim] maxval | sigma */
+    double prior_const;              /* sum of the (finite) priors of frozen parameters */
+
+    /* -- SZ geometry (SZ_data, joxsz_funcs.py:136-170) */
+    int32_t nr;                      /* len(r_pp) */
+    int32_t nt;                      /* sep: T_SZ is evaluated on r_pp[:nt] (joxsz_funcs.py:469) */
+    int32_t nmap;                    /* N: side of d_mat / filtering (odd) */
+    int32_t nh;                      /* H = N/2 + 1 */
+    int32_t npad;                    /* P: cyclic length of the beam convolution */
+    int32_t nseg;                    /* spline pieces referenced by the map */
+    const double*  r_pp;             /* [nr] kpc */
+    const double*  proj_op;          /* [4*nseg, nr]  pressure -> spline-piece coefficients of the Compton-y profile
+                                        (Abel transform * y scaling * not-a-knot fit; joxsz_funcs.py:457-460) */
+    const double*  y_op;             /* [nr, nr]      pressure -> Compton-y profile (joxsz_funcs.py:457-459) */
+    const int32_t* seg;              /* [H, H] spline piece of quarter-plane pixel (u, v) */
+    const double*  dx;               /* [H, H] offset from the piece's left knot */
+    const double*  bhat;             /* [P/2+1, P/2+1] beam spectrum * step^2 / P^2 */
+    const double*  cmat;             /* [H, H]  [v, kx]  w_v cos(2 pi kx v / N) */
+    const double*  hf;               /* [H, H]  [u, kx]  w_u sum_ky filt[ky,kx] cos(2 pi ky u / N) */
+    const double*  dinv;             /* [H, H]  [kx, v]  w_kx cos(2 pi kx v / N) / N^2 */
+    const double*  filt_q;           /* [H, H]  filtering[:H, :H] (full-map tap only) */
+    /* -- SZ tail (joxsz_funcs.py:469-479) */
+    const double*  w_t0;             /* [nt]  h(0) = w_t0 . t_prof */
+    int32_t nconv;
+    const double*  conv_T;           /* [nconv] keV   (joxsz_main.py:108-109) */
+    const double*  conv_I;           /* [nconv] 1e3 * I0 */
+    int32_t nd;                      /* SZ data points */
+    const double*  g_op;             /* [nd, H] spline through (radius[sep:], prof) evaluated at the data radii */
+    const double*  flux;             /* [nd] */
+    const double*  flux_err;         /* [nd] */
+
+    /* -- X-ray (mbproj2 Annuli / Band / CountRate; joxsz_funcs.py:184-211, 495-505) */
+    int32_t na;                      /* annuli = shells */
+    int32_t nb;                      /* energy bands */
+    int32_t ntab;                    /* temperature-table length */
+    const double*  midpt_kpc;        /* [na] */
+    const double*  projvols;         /* [na, na] annulus x shell, cm^3 */
+    const double*  tlog;             /* [ntab] ln T grid */
+    double tmin, tmax;               /* clip of T before ln */
+    const double*  lnrate0;          /* [nb, ntab] ln rate at Z = 0 */
+    const double*  lnrate1;          /* [nb, ntab] ln rate at Z = 1 */
+    const double*  cts;              /* [nb, na] observed counts; NaN = missing bin */
+    const double*  srcscale;         /* [nb, na] areascale * exposure */
+    const double*  bkgterm;          /* [nb, na] backrate * geomarea * areascale * exposure (x backscale) */
+} jx_setup;
+
+typedef struct jx_handle jx_handle;
+
+/* Build a handle: validates the geometry, copies every constant to the device, sizes the workspace. */
+int  jx_create(const jx_setup* setup, jx_handle** out);
+void jx_destroy(jx_handle* h);
+/* Message of the last failure on this handle (h may be NULL: last jx_create failure). */
+const char* jx_last_error(const jx_handle* h);
+
+/* THE hot path: replaces one emcee batch of `getLikelihood` calls (joxsz_funcs.py:507-546).
+ * theta [W, ndim] -> ll [W]; -inf exactly where the reference returns -inf; never NaN. */
+int jx_loglike(jx_handle* h, const double* theta, int32_t W, double* ll, void* stream);
+
+/* ---- parity taps: every output pointer may be NULL (not produced).  Taps evaluate every walker,
+ *      like the reference's component methods, regardless of prior flags. */
+
+/* K1: pressure on r_pp (`get_sz_like('pp')`, joxsz_funcs.py:453), T_SZ on r_pp[:nt] (:469),
+ * n_e and T_X at the annulus mid-points (:338-339, mbproj2 computeProfs), status bits, summed prior. */
+int jx_profiles(jx_handle* h, const double* theta, int32_t W,
+                double* pp /*[W,nr]*/, double* tsz /*[W,nt]*/, double* ne_ann /*[W,na]*/,
+                double* tx_ann /*[W,na]*/, uint32_t* flags /*[W]*/, double* prior /*[W]*/, void* stream);
+
+/* K2: Compton-y profile (joxsz_funcs.py:457-459) and the spline-piece coefficients the map uses. */
+int jx_sz_project(jx_handle* h, const double* theta, int32_t W,
+                  double* y /*[W,nr]*/, double* coef /*[W,4*nseg]*/, void* stream);
+
+/* K3 full maps: y_2d (:462), conv_2d (:464), map_out (:466-467), each [W, N, N]. */
+int jx_sz_maps(jx_handle* h, const double* theta, int32_t W,
+               double* y2d, double* conv2d, double* mapout, void* stream);
+
+/* K3+K5: filtered row map_out[N//2, N//2:] [W,H]; `get_sz_like('bright')` [W,H] (:472-473);
+ * model at the data radii [W,nd] (:476); chisq [W] (:478). */
+int jx_sz_profile(jx_handle* h, const double* theta, int32_t W,
+                  double* row, double* bright, double* model, double* chisq, void* stream);
+
+/* K4: predicted X-ray profiles (`Fit.calcProfiles`, :527) [W,nb,na] and the Cash log-likelihood
+ * (`mylikeFromProfs`, :495-505; -inf where a profile is not > 0, :529-532) [W]. */
+int jx_xray(jx_handle* h, const double* theta, int32_t W, double* pred, double* cash, void* stream);
+
+/* Component methods at arbitrary radii (press_fun :275, press_derivative :289, vikhFunction :375,
+ * temp_fun :321, mass_fun :428).  No handle: `pars` [W, JX_NPAR] holds full parameter vectors.
+ * Outputs [W, n] each, NULL to skip. */
+int jx_radial_profiles(const double* pars, int32_t W, int32_t dens_mode, const double* r, int32_t n,
+                       double mu_gas, double* press, double* dpress, double* ne, double* tsz, double* tx,
+                       double* mass, int32_t device, void* stream);
+
+/* ---- ensemble stretch move (emcee RedBlueMove/StretchMove semantics; joxsz_main.py:206-210).
+ * The ensemble has `nall` walkers; `coords` [nall, ndim] is the gathered ensemble (identical on every
+ * rank); walkers [first, first+count) are local to this rank.  `perm` [nall] is a random permutation of
+ * 0..nall-1 shared by all ranks and `pos` [nall] its inverse; the colour of walker i is pos[i] & 1
+ * (emcee: `inds = arange(n) % 2; shuffle(inds)`).  For each local walker of colour `split`: partner
+ * j = perm[2 r + (1 - split)] with r uniform over the other colour, z = ((a-1) u + 1)^2 / a,
+ * prop = c_j - (c_j - s) z, factor = (ndim-1) ln z, active = 1.  Walkers of the other colour get their
+ * current position, factor 0 and active = 0.  RNG: Philox4x32-10, key = seed, counter = (global
+ * walker index, iteration, split, purpose), so draws do not depend on how walkers are sharded. */
+int jx_stretch_propose(const double* coords, const int32_t* perm, const int32_t* pos, int32_t nall, int32_t ndim,
+                       int32_t first, int32_t count, int32_t split, double a, uint64_t seed, uint64_t iteration,
+                       double* prop /*[count,ndim]*/, double* factor /*[count]*/, int32_t* active /*[count]*/,
+                       int32_t device, void* stream);
+/* Accept where active and factor + lp_new - lp_old > ln(u): copies prop/lp_new over coords_local
+ * [count, ndim] / lp_local [count] and increments naccept [count] (emcee RedBlueMove.propose). */
+int jx_stretch_accept(double* coords_local, double* lp_local, const double* prop, const double* lp_new,
+                      const double* factor, const int32_t* active, int32_t ndim, int32_t first, int32_t count,
+                      int32_t split, uint64_t seed, uint64_t iteration, int32_t* naccept, int32_t device,
+                      void* stream);
+
+/* ---- measurement helpers (bench.py) */
+enum jx_stage { JX_ST_PROFILES = 0, JX_ST_PROJECT, JX_ST_SZMAP, JX_ST_XRAY, JX_NSTAGE };
+/* When on, jx_loglike brackets each stage with CUDA events on `stream`. */
+int jx_set_profiling(jx_handle* h, int32_t on);
+/* Sum of per-stage device milliseconds and launch counts since the last reset [host outputs]; resets. */
+int jx_stage_times(jx_handle* h, double* ms /*[JX_NSTAGE]*/, int64_t* launches /*[JX_NSTAGE]*/);
+/* Sustained FP64 FMA throughput of the device in TFLOP/s (a dependent-chain-free DFMA loop). */
+int jx_measure_fp64_tflops(int32_t device, double* tflops);
+/* Library build info (arch, ABI). */
+const char* jx_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JOXSZ_B200_H */

@@ -1,0 +1,452 @@
+// C ABI of libjoxsz_b200.so (see include/joxsz_b200.h): handle life cycle, the batched likelihood
+// entry point, parity taps and measurement helpers.  No CPU fallback anywhere: every compute entry
+// launches the CUDA kernels or fails with a status code.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "jx_common.cuh"
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+int fail(jx_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+int cuda_fail(jx_handle* h, cudaError_t e, const char* where) {
+    return fail(h, JX_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+
+#define JX_CUDA(h, call)                                         \
+    do {                                                         \
+        cudaError_t e_ = (call);                                 \
+        if (e_ != cudaSuccess) return cuda_fail(h, e_, #call);   \
+    } while (0)
+
+template <class T>
+int dev_alloc(jx_handle* h, T** out, size_t count) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc");
+    if (h->nallocs >= (int)(sizeof(h->allocs) / sizeof(h->allocs[0]))) {
+        cudaFree(p);
+        return fail(h, JX_ERR_INVALID, "allocation table full");
+    }
+    h->allocs[h->nallocs++] = p;
+    *out = static_cast<T*>(p);
+    return JX_OK;
+}
+
+template <class T>
+int upload(jx_handle* h, const T** out, const T* host, size_t count) {
+    T* p = nullptr;
+    int rc = dev_alloc(h, &p, count);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMemcpy H2D");
+    *out = p;
+    return JX_OK;
+}
+
+// [rows, cols] -> [rows, ld] zero padded
+int upload_padded(jx_handle* h, const double** out, const double* host, int rows, int cols, int ld) {
+    std::vector<double> tmp((size_t)rows * ld, 0.0);
+    for (int r = 0; r < rows; ++r) memcpy(&tmp[(size_t)r * ld], host + (size_t)r * cols, sizeof(double) * cols);
+    return upload(h, out, tmp.data(), tmp.size());
+}
+
+int check_ready(jx_handle* h, const double* theta, int W) {
+    if (!h) return JX_ERR_INVALID;
+    if (!theta || W < 0) return fail(h, JX_ERR_INVALID, "theta is NULL or W < 0");
+    if (W > h->d.max_walkers) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "W = %d exceeds max_walkers = %d", W, h->d.max_walkers);
+        return fail(h, JX_ERR_CAPACITY, buf);
+    }
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+    return JX_OK;
+}
+
+void flush_stage_events(jx_handle* h) {
+    if (!h->pending) return;
+    cudaEventSynchronize(h->ev[JX_NSTAGE]);
+    // execution order: profiles, xray, project, szmap
+    static const int order[JX_NSTAGE] = {JX_ST_PROFILES, JX_ST_XRAY, JX_ST_PROJECT, JX_ST_SZMAP};
+    for (int i = 0; i < JX_NSTAGE; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) {
+            h->stage_ms[order[i]] += ms;
+            h->stage_launches[order[i]] += 1;
+        }
+    }
+    h->pending = false;
+}
+
+}  // namespace
+
+extern "C" const char* jx_build_info(void) {
+    return "libjoxsz_b200 abi=" "3" " arch=sm_100a fp64 K1=profiles K2=dmma-project K3=fft256-szmap K4=xray";
+}
+
+extern "C" const char* jx_last_error(const jx_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" void jx_destroy(jx_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (int i = 0; i < h->nallocs; ++i) cudaFree(h->allocs[i]);
+    if (h->d.ws_convq) cudaFree(h->d.ws_convq);
+    if (h->tap_scratch) cudaFree(h->tap_scratch);
+    if (h->ev_ready)
+        for (auto& e : h->ev) cudaEventDestroy(e);
+    delete h;
+}
+
+extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
+    if (!s || !out) return fail(nullptr, JX_ERR_INVALID, "NULL setup or output pointer");
+    *out = nullptr;
+    if (s->abi_version != JX_ABI_VERSION) return fail(nullptr, JX_ERR_INVALID, "jx_setup.abi_version mismatch");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, JX_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
+    if (s->device < 0 || s->device >= ndev) return fail(nullptr, JX_ERR_NO_DEVICE, "device ordinal out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, s->device) != cudaSuccess)
+        return fail(nullptr, JX_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major < 10)
+        return fail(nullptr, JX_ERR_NO_DEVICE, std::string("device is ") + prop.name + " (sm_" +
+                    std::to_string(prop.major) + std::to_string(prop.minor) + "); sm_100 (B200) required");
+
+    // ---- validate sizes
+    auto bad = [&](const char* m) { return fail(nullptr, JX_ERR_INVALID, m); };
+    if (s->ndim < 1 || s->ndim > JX_MAX_NDIM) return bad("ndim must be in 1..32");
+    if (s->max_walkers < 1) return bad("max_walkers must be >= 1");
+    if (s->nr < 4) return bad("nr must be >= 4");
+    if (s->nmap < 3 || (s->nmap & 1) == 0) return bad("nmap must be odd (maps built by the reference have side 2m+1)");
+    if (s->nh != s->nmap / 2 + 1) return bad("nh must equal nmap/2 + 1");
+    if (s->nt != s->nh - 1) return bad("nt (sep) must equal nh - 1 (joxsz_funcs.py:469-473)");
+    if (s->nt > s->nr) return bad("sep exceeds len(r_pp)");
+    if (s->npad != 256) return bad("only cyclic length P = 256 is implemented by the map kernel");
+    if (s->nh > s->npad / 2 + 1) return bad("map quarter plane does not fit the cyclic length");
+    if (s->nseg < 1 || s->nseg > 65535) return bad("nseg out of range");
+    if (s->na < 1 || s->na > 32) return bad("1..32 annuli supported (one lane per annulus)");
+    if (s->nb < 1 || s->ntab < 2 || s->nd < 1 || s->nconv < 2) return bad("empty X-ray / SZ data tables");
+    for (int i = 0; i < JX_NPAR; ++i)
+        if (s->slot_src[i] >= s->ndim) return bad("slot_src refers to a column beyond ndim");
+    const void* required[] = {s->prior_kind, s->prior_a, s->prior_b, s->r_pp, s->proj_op, s->y_op, s->seg, s->dx,
+                              s->bhat, s->cmat, s->hf, s->dinv, s->filt_q, s->w_t0, s->conv_T, s->conv_I, s->g_op,
+                              s->flux, s->flux_err, s->midpt_kpc, s->projvols, s->tlog, s->lnrate0, s->lnrate1,
+                              s->cts, s->srcscale, s->bkgterm};
+    for (const void* p : required)
+        if (!p) return bad("a required jx_setup array is NULL");
+    if (!std::isfinite(s->prior_const)) return bad("prior_const is not finite (a frozen parameter is outside its prior)");
+    for (int i = 0; i < s->nh * s->nh; ++i)
+        if (s->seg[i] < 0 || s->seg[i] >= s->nseg) return bad("seg entry outside 0..nseg-1");
+
+    JX_CUDA(nullptr, cudaSetDevice(s->device));
+    jx_handle* h = new (std::nothrow) jx_handle();
+    if (!h) return bad("out of host memory");
+    h->device = s->device;
+    h->sm_count = prop.multiProcessorCount;
+    h->nallocs = 0;
+    h->convq_capacity = 0;
+    h->tap_scratch = nullptr;
+    h->tap_scratch_walkers = 0;
+    h->profiling = 0;
+    h->ev_ready = false;
+    h->pending = false;
+    memset(h->stage_ms, 0, sizeof h->stage_ms);
+    memset(h->stage_launches, 0, sizeof h->stage_launches);
+    jx_dev& d = h->d;
+    memset(&d, 0, sizeof d);
+
+    d.ndim = s->ndim; d.dens_mode = s->dens_mode; d.exclude_mass = s->exclude_unphy_mass;
+    memcpy(d.slot_src, s->slot_src, sizeof d.slot_src);
+    memcpy(d.slot_val, s->slot_val, sizeof d.slot_val);
+    d.prior_const = s->prior_const;
+    d.nr = s->nr; d.nrp = (s->nr + 7) & ~7; d.nt = s->nt; d.nmap = s->nmap; d.nh = s->nh; d.npad = s->npad;
+    d.nq = s->npad / 2 + 1; d.nseg = s->nseg; d.ncoef = 4 * s->nseg;
+    d.hp8 = (s->nh + 7) & ~7; d.hp16 = (s->nh + 15) & ~15;
+    d.nconv = s->nconv; d.nd = s->nd; d.na = s->na; d.nb = s->nb; d.ntab = s->ntab;
+    d.tmin = s->tmin; d.tmax = s->tmax; d.max_walkers = s->max_walkers;
+
+    int rc = JX_OK;
+#define UP(field, src, count) if (!rc) rc = upload(h, &d.field, src, (size_t)(count))
+    const int H = s->nh, Q = d.nq;
+    UP(prior_kind, s->prior_kind, s->ndim);
+    UP(prior_a, s->prior_a, s->ndim);
+    UP(prior_b, s->prior_b, s->ndim);
+    UP(r_pp, s->r_pp, s->nr);
+    if (!rc) rc = upload_padded(h, &d.proj_op, s->proj_op, d.ncoef, s->nr, d.nrp);
+    if (!rc) rc = upload_padded(h, &d.y_op, s->y_op, s->nr, s->nr, d.nrp);
+    UP(seg, s->seg, H * H);
+    UP(dx, s->dx, H * H);
+    UP(bhat, s->bhat, Q * Q);
+    UP(hf, s->hf, H * H);
+    UP(dinv, s->dinv, H * H);
+    UP(filt_q, s->filt_q, H * H);
+    UP(w_t0, s->w_t0, s->nt);
+    UP(conv_T, s->conv_T, s->nconv);
+    UP(conv_I, s->conv_I, s->nconv);
+    UP(g_op, s->g_op, s->nd * H);
+    UP(flux, s->flux, s->nd);
+    UP(flux_err, s->flux_err, s->nd);
+    UP(midpt_kpc, s->midpt_kpc, s->na);
+    UP(projvols, s->projvols, s->na * s->na);
+    UP(tlog, s->tlog, s->ntab);
+    UP(lnrate0, s->lnrate0, s->nb * s->ntab);
+    UP(lnrate1, s->lnrate1, s->nb * s->ntab);
+    UP(cts, s->cts, s->nb * s->na);
+    UP(srcscale, s->srcscale, s->nb * s->na);
+    UP(bkgterm, s->bkgterm, s->nb * s->na);
+#undef UP
+    // derived tables
+    if (!rc) {
+        std::vector<double> t((size_t)H * H);
+        for (int v = 0; v < H; ++v)
+            for (int k = 0; k < H; ++k) t[(size_t)k * H + v] = s->cmat[(size_t)v * H + k];
+        rc = upload(h, &d.cmat_t, t.data(), t.size());
+    }
+    if (!rc) {
+        std::vector<uint16_t> s16((size_t)H * H);
+        for (int i = 0; i < H * H; ++i) s16[i] = (uint16_t)s->seg[i];
+        rc = upload(h, &d.seg16, s16.data(), s16.size());
+    }
+    if (!rc) {
+        std::vector<double> c(s->nmap);
+        for (int m = 0; m < s->nmap; ++m) c[m] = cos(2.0 * M_PI * (double)m / (double)s->nmap);
+        rc = upload(h, &d.costab, c.data(), c.size());
+    }
+    if (!rc) {
+        std::vector<double> t((size_t)d.hp8 * d.hp8, 0.0);
+        for (int u = 0; u < H; ++u) memcpy(&t[(size_t)u * d.hp8], s->hf + (size_t)u * H, sizeof(double) * H);
+        rc = upload(h, &d.hf_pad, t.data(), t.size());
+    }
+    // workspace
+    const size_t Wm = (size_t)s->max_walkers;
+    if (!rc) rc = dev_alloc(h, &d.ws_pp, Wm * d.nrp);
+    if (!rc) rc = dev_alloc(h, &d.ws_tsz, Wm * d.nt);
+    if (!rc) rc = dev_alloc(h, &d.ws_ne, Wm * d.na);
+    if (!rc) rc = dev_alloc(h, &d.ws_tx, Wm * d.na);
+    if (!rc) rc = dev_alloc(h, &d.ws_prior, Wm);
+    if (!rc) rc = dev_alloc(h, &d.ws_xlike, Wm);
+    if (!rc) rc = dev_alloc(h, &d.ws_flags, Wm);
+    if (!rc) rc = dev_alloc(h, &d.ws_coef, Wm * d.ncoef);
+    if (!rc) rc = dev_alloc(h, &d.ws_row, Wm * d.nh);
+    if (!rc) {
+        size_t smem = jx_szmap_smem_bytes(d);
+        if (smem > (size_t)prop.sharedMemPerBlockOptin) {
+            rc = fail(h, JX_ERR_INVALID, "map kernel needs more shared memory than the device offers");
+        } else {
+            cudaError_t e = jx_szmap_configure(d);
+            if (e != cudaSuccess) rc = cuda_fail(h, e, "configure map kernel");
+        }
+    }
+    if (rc) {
+        g_create_error = h->err;
+        jx_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return JX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the hot path
+// ------------------------------------------------------------------------------------------------
+extern "C" int jx_loglike(jx_handle* h, const double* theta, int32_t W, double* ll, void* stream) {
+    int rc = check_ready(h, theta, W);
+    if (rc) return rc;
+    if (!ll) return fail(h, JX_ERR_INVALID, "ll is NULL");
+    if (W == 0) return JX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    jx_dev& d = h->d;
+    const bool prof = h->profiling != 0;
+    if (prof) {
+        if (!h->ev_ready) {
+            for (auto& e : h->ev) JX_CUDA(h, cudaEventCreate(&e));
+            h->ev_ready = true;
+        }
+        flush_stage_events(h);
+        JX_CUDA(h, cudaEventRecord(h->ev[0], st));
+    }
+    JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, d.ws_tsz, d.ws_ne, d.ws_tx, d.ws_flags, d.ws_prior, st));
+    if (prof) JX_CUDA(h, cudaEventRecord(h->ev[1], st));
+    JX_CUDA(h, jx_launch_xray(d, theta, d.ws_ne, d.ws_tx, W, nullptr, d.ws_xlike, d.ws_flags, st));
+    if (prof) JX_CUDA(h, cudaEventRecord(h->ev[2], st));
+    JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op, d.ncoef, d.ws_coef, st));
+    if (prof) JX_CUDA(h, cudaEventRecord(h->ev[3], st));
+    JX_CUDA(h, jx_launch_szmap(d, theta, d.ws_coef, d.ws_tsz, d.ws_flags, d.ws_prior, d.ws_xlike, W, h->sm_count,
+                               nullptr, nullptr, nullptr, nullptr, nullptr, ll, st));
+    if (prof) {
+        JX_CUDA(h, cudaEventRecord(h->ev[4], st));
+        h->pending = true;
+    }
+    return JX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parity taps
+// ------------------------------------------------------------------------------------------------
+extern "C" int jx_profiles(jx_handle* h, const double* theta, int32_t W, double* pp, double* tsz, double* ne_ann,
+                           double* tx_ann, uint32_t* flags, double* prior, void* stream) {
+    int rc = check_ready(h, theta, W);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    jx_dev& d = h->d;
+    // X-ray positivity is part of the status bits: run K1 into the workspace copies K4 needs
+    JX_CUDA(h, jx_launch_profiles(d, theta, W, pp, d.nr, tsz, d.ws_ne, d.ws_tx, d.ws_flags, prior, st));
+    JX_CUDA(h, jx_launch_xray(d, theta, d.ws_ne, d.ws_tx, W, nullptr, nullptr, d.ws_flags, st));
+    if (ne_ann) JX_CUDA(h, cudaMemcpyAsync(ne_ann, d.ws_ne, sizeof(double) * W * d.na, cudaMemcpyDeviceToDevice, st));
+    if (tx_ann) JX_CUDA(h, cudaMemcpyAsync(tx_ann, d.ws_tx, sizeof(double) * W * d.na, cudaMemcpyDeviceToDevice, st));
+    if (flags) JX_CUDA(h, cudaMemcpyAsync(flags, d.ws_flags, sizeof(uint32_t) * W, cudaMemcpyDeviceToDevice, st));
+    return JX_OK;
+}
+
+extern "C" int jx_sz_project(jx_handle* h, const double* theta, int32_t W, double* y, double* coef, void* stream) {
+    int rc = check_ready(h, theta, W);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    jx_dev& d = h->d;
+    JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+    if (y) JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.y_op, d.nr, y, st));
+    if (coef) JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op, d.ncoef, coef, st));
+    return JX_OK;
+}
+
+static int ensure_convq(jx_handle* h, int W) {
+    if (h->convq_capacity >= (size_t)W) return JX_OK;
+    if (h->d.ws_convq) cudaFree(h->d.ws_convq);
+    h->d.ws_convq = nullptr;
+    h->convq_capacity = 0;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, sizeof(double) * (size_t)W * h->d.nh * h->d.nh);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc(convq tap)");
+    h->d.ws_convq = (double*)p;
+    h->convq_capacity = W;
+    return JX_OK;
+}
+
+extern "C" int jx_sz_maps(jx_handle* h, const double* theta, int32_t W, double* y2d, double* conv2d, double* mapout,
+                          void* stream) {
+    int rc = check_ready(h, theta, W);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    jx_dev& d = h->d;
+    JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, d.ws_tsz, nullptr, nullptr, nullptr, nullptr, st));
+    JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op, d.ncoef, d.ws_coef, st));
+    if (y2d) JX_CUDA(h, jx_launch_tap_y2d(d, d.ws_coef, W, y2d, st));
+    if (conv2d || mapout) {
+        if ((rc = ensure_convq(h, W))) return rc;
+        JX_CUDA(h, jx_launch_szmap(d, theta, d.ws_coef, d.ws_tsz, nullptr, nullptr, nullptr, W, h->sm_count,
+                                   d.ws_convq, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+        if (conv2d) JX_CUDA(h, jx_launch_tap_expand(d, d.ws_convq, W, conv2d, st));
+        if (mapout) {
+            if (h->tap_scratch_walkers < (size_t)W) {
+                if (h->tap_scratch) cudaFree(h->tap_scratch);
+                h->tap_scratch = nullptr;
+                h->tap_scratch_walkers = 0;
+                void* p = nullptr;
+                JX_CUDA(h, cudaMalloc(&p, sizeof(double) * 2 * (size_t)W * d.nh * d.nh));
+                h->tap_scratch = (double*)p;
+                h->tap_scratch_walkers = W;
+            }
+            JX_CUDA(h, jx_launch_tap_mapout(d, d.ws_convq, W, mapout, h->tap_scratch, st));
+        }
+    }
+    return JX_OK;
+}
+
+extern "C" int jx_sz_profile(jx_handle* h, const double* theta, int32_t W, double* row, double* bright,
+                             double* model, double* chisq, void* stream) {
+    int rc = check_ready(h, theta, W);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    jx_dev& d = h->d;
+    JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, d.ws_tsz, nullptr, nullptr, nullptr, nullptr, st));
+    JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op, d.ncoef, d.ws_coef, st));
+    JX_CUDA(h, jx_launch_szmap(d, theta, d.ws_coef, d.ws_tsz, nullptr, nullptr, nullptr, W, h->sm_count, nullptr,
+                               row, bright, model, chisq, nullptr, st));
+    return JX_OK;
+}
+
+extern "C" int jx_xray(jx_handle* h, const double* theta, int32_t W, double* pred, double* cash, void* stream) {
+    int rc = check_ready(h, theta, W);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    jx_dev& d = h->d;
+    JX_CUDA(h, jx_launch_profiles(d, theta, W, nullptr, d.nr, nullptr, d.ws_ne, d.ws_tx, nullptr, nullptr, st));
+    JX_CUDA(h, jx_launch_xray(d, theta, d.ws_ne, d.ws_tx, W, pred, cash, nullptr, st));
+    return JX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// measurement helpers
+// ------------------------------------------------------------------------------------------------
+extern "C" int jx_set_profiling(jx_handle* h, int32_t on) {
+    if (!h) return JX_ERR_INVALID;
+    if (!on && h->pending) flush_stage_events(h);
+    h->profiling = on;
+    return JX_OK;
+}
+
+extern "C" int jx_stage_times(jx_handle* h, double* ms, int64_t* launches) {
+    if (!h || !ms || !launches) return JX_ERR_INVALID;
+    cudaSetDevice(h->device);
+    flush_stage_events(h);
+    for (int i = 0; i < JX_NSTAGE; ++i) {
+        ms[i] = h->stage_ms[i];
+        launches[i] = h->stage_launches[i];
+        h->stage_ms[i] = 0.0;
+        h->stage_launches[i] = 0;
+    }
+    return JX_OK;
+}
+
+namespace {
+__global__ void fp64_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+}  // namespace
+
+extern "C" int jx_measure_fp64_tflops(int32_t device, double* tflops) {
+    if (!tflops) return JX_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return JX_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    double* buf = nullptr;
+    if (cudaMalloc(&buf, sizeof(double) * blocks * threads) != cudaSuccess) return JX_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    fp64_peak_kernel<<<blocks, threads>>>(buf, iters);   // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(buf, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    cudaError_t e = cudaGetLastError();
+    *tflops = best;
+    return e == cudaSuccess ? JX_OK : JX_ERR_CUDA;
+}

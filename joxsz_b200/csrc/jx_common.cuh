@@ -1,0 +1,122 @@
+// Internal declarations shared by the kernels of libjoxsz_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <string>
+
+#include "../../include/joxsz_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libjoxsz_b200 is written for sm_100a (B200) only"
+#endif
+
+#define JX_HD __host__ __device__ __forceinline__
+#define JX_D __device__ __forceinline__
+
+constexpr int JX_WARP = 32;
+constexpr int JX_MAX_NDIM = 32;   // theta columns handled by one warp
+
+// Device-resident constants + workspace of one handle.
+struct jx_dev {
+    // parameters
+    int ndim, dens_mode, exclude_mass;
+    int slot_src[JX_NPAR];
+    double slot_val[JX_NPAR];
+    const int32_t* prior_kind;
+    const double *prior_a, *prior_b;
+    double prior_const;
+    // SZ geometry
+    int nr, nrp /* nr rounded up to 8: leading dimension of ws_pp and the operators */, nt, nmap, nh, npad, nq, nseg,
+        ncoef /* 4*nseg */;
+    const double* r_pp;
+    const double* proj_op;   // [ncoef, nrp] zero padded
+    const double* y_op;      // [nr, nrp] zero padded
+    const int32_t* seg;      // [nh, nh]
+    const double* dx;        // [nh, nh]
+    const double* bhat;      // [nq, nq]
+    const double* cmat_t;    // [nh, nh] transposed on upload: [kx, v]
+    const double* hf;        // [nh, nh] [u, kx]
+    const double* dinv;      // [nh, nh] [kx, v]
+    const double* filt_q;    // [nh, nh]
+    // derived at jx_create
+    int hp8, hp16;           // nh rounded up to 8 / 16
+    const uint16_t* seg16;   // [nh, nh] seg narrowed
+    const double* costab;    // [nmap] cos(2 pi m / nmap)
+    const double* hf_pad;    // [hp8, hp8] hf zero padded
+    const double* w_t0;      // [nt]
+    int nconv;
+    const double *conv_T, *conv_I;
+    int nd;
+    const double *g_op, *flux, *flux_err;
+    // X-ray
+    int na, nb, ntab;
+    const double *midpt_kpc, *projvols, *tlog, *lnrate0, *lnrate1, *cts, *srcscale, *bkgterm;
+    double tmin, tmax;
+    // workspace [max_walkers, ...]
+    int max_walkers;
+    double* ws_pp;      // [W, nrp] zero padded
+    double* ws_tsz;     // [W, nt]
+    double* ws_ne;      // [W, na]
+    double* ws_tx;      // [W, na]
+    double* ws_prior;   // [W]
+    double* ws_xlike;   // [W]
+    uint32_t* ws_flags; // [W]
+    double* ws_coef;    // [W, ncoef]
+    double* ws_row;     // [W, nh]
+    double* ws_convq;   // tap only, allocated lazily: [W, nh, nh]
+};
+
+struct jx_handle {
+    jx_dev d;
+    int device;
+    int sm_count;
+    std::string err;
+    void* allocs[64];
+    int nallocs;
+    size_t convq_capacity;   // walkers for which ws_convq is allocated
+    double* tap_scratch;     // full-map tap scratch [W, 2, nh, nh]
+    size_t tap_scratch_walkers;
+    // profiling
+    int profiling;
+    cudaEvent_t ev[JX_NSTAGE + 1];
+    bool ev_ready;
+    double stage_ms[JX_NSTAGE];
+    int64_t stage_launches[JX_NSTAGE];
+    bool pending;            // events recorded but not yet accumulated
+    int pending_launches[JX_NSTAGE];
+};
+
+// ---- launchers implemented by the kernel files (all asynchronous on `st`)
+cudaError_t jx_launch_profiles(const jx_dev& d, const double* theta, int W, double* pp, int ld_pp, double* tsz,
+                               double* ne_ann, double* tx_ann, uint32_t* flags, double* prior, cudaStream_t st);
+cudaError_t jx_launch_project(const jx_dev& d, const double* pp, int W, const double* op, int nout,
+                              double* out, cudaStream_t st);
+cudaError_t jx_launch_xray(const jx_dev& d, const double* theta, const double* ne_ann, const double* tx_ann,
+                           int W, double* pred, double* cash, uint32_t* flags, cudaStream_t st);
+// production map stage: coef -> filtered row (+ optional quarter-plane convolved map), and the tail.
+// `flags` may be NULL (evaluate every walker).  ll may be NULL (taps).
+cudaError_t jx_launch_szmap(const jx_dev& d, const double* theta, const double* coef, const double* tsz,
+                            const uint32_t* flags, const double* prior, const double* xlike, int W, int sm_count,
+                            double* convq, double* row, double* bright, double* model, double* chisq, double* ll,
+                            cudaStream_t st);
+cudaError_t jx_szmap_configure(const jx_dev& d);   // one-time cudaFuncSetAttribute
+cudaError_t jx_launch_tap_y2d(const jx_dev& d, const double* coef, int W, double* y2d, cudaStream_t st);
+cudaError_t jx_launch_tap_expand(const jx_dev& d, const double* convq, int W, double* conv2d, cudaStream_t st);
+cudaError_t jx_launch_tap_mapout(const jx_dev& d, const double* convq, int W, double* mapout, double* scratch,
+                                 cudaStream_t st);
+size_t jx_szmap_smem_bytes(const jx_dev& d);
+
+// ---- small device helpers
+JX_D double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+JX_D double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+JX_D double jx_neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }

@@ -1,0 +1,536 @@
+// K3 (+K5) -- Compton-y map synthesis, beam convolution, transfer-function filtering and the
+// chi-square tail, one persistent CTA per SM looping over walkers; the whole map pipeline of a walker
+// lives in shared memory.
+//
+// Replaces, per walker, reference joxsz_funcs.py:462 (y_2d = f(d_mat)), :464 (fftconvolve 'same'),
+// :466-467 (fft2 * filtering, ifft2), :469-479 (T_SZ conversion, calibration, spline to the data radii,
+// chi^2) and :538 (sum of the three terms).
+//
+// Geometry facts used (checked at pack time, joxsz_b200/operators.py): the map side N is odd and the
+// Compton-y map, the beam and the filter are symmetric under x -> -x, y -> -y about the centre pixel.
+// Re-centred on the origin every 2-D DFT of the stage is therefore a REAL cosine transform of the
+// quarter plane (H = N/2+1 rows/cols), and two real even sequences ride in one complex FFT (real part /
+// imaginary part) with no post-processing.  Per walker:
+//
+//   A  rows    Z[u,:]  (spline pieces evaluated on the fly)  --FFT256-->  xs[u, kx]      kx = 0..P/2
+//   B  columns xs[:, kx] --FFT256--> * bhat[ky, kx] --FFT256--> xs[u, kx]            (beam, cyclic length P)
+//   C  rows    xs[u, :]  --FFT256--> conv_c[u, v]  (in place)     = fftconvolve(y_2d, beam,'same')*step^2
+//   D  G[kx] = sum_u hf[u,kx] * sum_v conv_c[u,v] w_v cos(2 pi kx v / N)      FP64 tensor cores (DMMA)
+//   E  row[v] = 1/N^2 sum_kx w_kx cos(2 pi kx v / N) G[kx]                    = map_out[N//2, N//2 + v]
+//   F  bright = row * convert([h(0), T_SZ]) * calibration; model = g_op @ bright; chi^2; log-likelihood
+//
+// D+E are the exact length-N circular filter (N = 171 = 9*19 for the shipped cluster, so a dense
+// cosine transform), reduced over ky analytically because only the central row is consumed.
+// The per-walker inputs (spline coefficients) arrive by TMA bulk copy (cp.async.bulk + mbarrier),
+// double buffered against the previous walker's compute.
+#include "jx_fft.cuh"
+
+namespace {
+
+constexpr int K3_THREADS = 256;
+constexpr int K3_GROUPS = K3_THREADS / 16;
+constexpr int K3_P = 256;
+constexpr int K3_Q = K3_P / 2 + 1;       // 129
+constexpr int K3_XS = 130;               // row pitch of xs (doubles): XS/2 odd -> conflict-free column walks
+constexpr int K3_MAXUT = 9;              // u-tiles per phase-D item (H <= 129 -> 17 tiles -> 9 per half)
+
+struct k3_args {
+    jx_dev d;
+    const double *theta, *coef, *tsz, *prior, *xlike;
+    const uint32_t* flags;
+    int W;
+    double *convq, *row, *bright, *model, *chisq, *ll;
+};
+
+struct k3_smem_layout {
+    size_t tw, xbuf, xs, coef, tsz, tarr, out, outp, gpart, bright, model, costab, mbar, total;
+};
+
+__host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8) {
+    k3_smem_layout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~size_t(15); return at; };
+    L.tw = take(256 * sizeof(double2));
+    L.xbuf = take((size_t)K3_GROUPS * JX_XB_ELEMS * sizeof(double2));
+    L.xs = take((size_t)hp8 * K3_XS * sizeof(double));
+    L.coef = take((size_t)2 * d.ncoef * sizeof(double));
+    L.tsz = take((size_t)(d.nt + 1) * sizeof(double));
+    L.tarr = take((size_t)(d.nh + 1) * sizeof(double));
+    L.out = take((size_t)hp8 * sizeof(double));
+    L.outp = take((size_t)2 * hp8 * sizeof(double));
+    L.gpart = take((size_t)2 * hp8 * sizeof(double));
+    L.bright = take((size_t)hp8 * sizeof(double));
+    L.model = take((size_t)(d.nd + 1) * sizeof(double));
+    L.costab = take((size_t)d.nmap * sizeof(double));
+    L.mbar = take(2 * sizeof(uint64_t));
+    L.total = o;
+    return L;
+}
+
+JX_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+JX_D void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+JX_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+JX_D void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+JX_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "JX_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra JX_DONE;\n"
+        "bra JX_WAIT;\n"
+        "JX_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+JX_D void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// value of the Compton-y spline at quarter-plane pixel `pix` (Horner on the piece's coefficients)
+JX_D double spline_pixel(const double* __restrict__ c, int nseg, const uint16_t* __restrict__ seg16,
+                         const double* __restrict__ dx, int pix) {
+    const int s = __ldg(seg16 + pix);
+    const double t = __ldg(dx + pix);
+    return c[s] + t * (c[nseg + s] + t * (c[2 * nseg + s] + t * c[3 * nseg + s]));
+}
+
+// scipy interp1d(kind='linear', fill_value='extrapolate') on a small table
+JX_D double linear_extrap(double x, const double* __restrict__ xk, const double* __restrict__ yk, int n) {
+    int idx = 0;
+    for (int i = 0; i < n; ++i) idx += (__ldg(xk + i) < x) ? 1 : 0;    // searchsorted(side='left')
+    if (x != x) idx = n;
+    idx = idx < 1 ? 1 : (idx > n - 1 ? n - 1 : idx);
+    double x0 = __ldg(xk + idx - 1), x1 = __ldg(xk + idx), y0 = __ldg(yk + idx - 1), y1 = __ldg(yk + idx);
+    double slope = (y1 - y0) / (x1 - x0);
+    return slope * (x - x0) + y0;
+}
+
+__global__ void __launch_bounds__(K3_THREADS, 1) k3_szmap_kernel(const __grid_constant__ k3_args a) {
+    extern __shared__ __align__(128) unsigned char k3_raw[];
+    const jx_dev& d = a.d;
+    const int H = d.nh, N = d.nmap, nseg = d.nseg, hp8 = d.hp8, hp16 = d.hp16;
+    const k3_smem_layout L = k3_layout(d, hp8);
+    double2* tw_s = reinterpret_cast<double2*>(k3_raw + L.tw);
+    double2* xbuf_all = reinterpret_cast<double2*>(k3_raw + L.xbuf);
+    double* xs = reinterpret_cast<double*>(k3_raw + L.xs);
+    double* coef_s = reinterpret_cast<double*>(k3_raw + L.coef);
+    double* tsz_s = reinterpret_cast<double*>(k3_raw + L.tsz);
+    double* tarr_s = reinterpret_cast<double*>(k3_raw + L.tarr);
+    double* out_s = reinterpret_cast<double*>(k3_raw + L.out);
+    double* outp_s = reinterpret_cast<double*>(k3_raw + L.outp);
+    double* gpart_s = reinterpret_cast<double*>(k3_raw + L.gpart);
+    double* bright_s = reinterpret_cast<double*>(k3_raw + L.bright);
+    double* model_s = reinterpret_cast<double*>(k3_raw + L.model);
+    double* costab_s = reinterpret_cast<double*>(k3_raw + L.costab);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(k3_raw + L.mbar);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = tid >> 4, t = tid & 15;
+    const unsigned gmask = 0xffffu << (lane & 16);           // the 16 lanes of this FFT group
+    double2* xbuf = xbuf_all + (size_t)grp * JX_XB_ELEMS;
+    const uint32_t coef_bytes = (uint32_t)(d.ncoef * sizeof(double));
+
+    // ---- one-time set-up of the CTA
+    for (int i = tid; i < 256; i += K3_THREADS) fft256_make_twiddle(i, tw_s[i]);
+    for (int i = tid; i < hp8 * K3_XS; i += K3_THREADS) xs[i] = 0.0;
+    for (int i = tid; i < N; i += K3_THREADS) costab_s[i] = __ldg(d.costab + i);
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const int w_first = blockIdx.x;
+    if (tid == 0 && w_first < a.W) {
+        mbar_expect_tx(&mbar[0], coef_bytes);
+        tma_bulk_g2s(coef_s, a.coef + (size_t)w_first * d.ncoef, coef_bytes, &mbar[0]);
+    }
+
+    int it = 0;
+    for (int w = w_first; w < a.W; w += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const double* cf = coef_s + (size_t)buf * d.ncoef;
+        // prefetch the next walker's coefficients into the other buffer (its last readers finished
+        // phase A of the previous iteration, several block barriers ago)
+        {
+            const int wn = w + gridDim.x;
+            if (tid == 0 && wn < a.W) {
+                mbar_expect_tx(&mbar[buf ^ 1], coef_bytes);
+                tma_bulk_g2s(coef_s + (size_t)(buf ^ 1) * d.ncoef, a.coef + (size_t)wn * d.ncoef, coef_bytes,
+                             &mbar[buf ^ 1]);
+            }
+        }
+        const bool skip = a.flags && a.flags[w] != 0u;
+        if (tid < d.nt) tsz_s[tid] = a.tsz[(size_t)w * d.nt + tid];
+        for (int i = K3_THREADS + tid; i < d.nt; i += K3_THREADS) tsz_s[i] = a.tsz[(size_t)w * d.nt + i];
+        mbar_wait(&mbar[buf], (uint32_t)((it >> 1) & 1));
+        if (skip) {                         // block-uniform
+            if (tid == 0 && a.ll) a.ll[w] = jx_neg_inf();
+            __syncthreads();                // tsz_s reuse
+            continue;
+        }
+
+        double re[16], im[16];
+
+        // ================= phase A: synthesise map rows and transform them along x
+        const int npair = (H + 1) >> 1;
+        for (int rp = grp; rp < npair; rp += K3_GROUPS) {
+            const int u0 = 2 * rp, u1 = u0 + 1;
+            const bool has1 = u1 < H;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int f = fold256(t + 16 * j);
+                double vr = 0.0, vi = 0.0;
+                if (f < H) {
+                    vr = spline_pixel(cf, nseg, d.seg16, d.dx, u0 * H + f);
+                    if (has1) vi = spline_pixel(cf, nseg, d.seg16, d.dx, u1 * H + f);
+                }
+                re[j] = vr; im[j] = vi;
+            }
+            fft256_pass1(t, re, im, tw_s, xbuf);
+            __syncwarp(gmask);
+            fft256_pass2(t, re, im, xbuf);
+            __syncwarp(gmask);
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const int k = t + 16 * rev16(p);
+                if (k < K3_Q) {
+                    xs[u0 * K3_XS + k] = re[p];
+                    if (has1) xs[u1 * K3_XS + k] = im[p];
+                }
+            }
+        }
+        __syncthreads();
+
+        // ================= phase B: columns -- cyclic convolution with the beam along y
+        const int ncpair = (K3_Q + 1) >> 1;
+        for (int cp = grp; cp < ncpair; cp += K3_GROUPS) {
+            const int kx = 2 * cp;
+            const bool has1 = kx + 1 < K3_Q;
+            double2 bh[16];
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const int f = fold256(t + 16 * rev16(p));
+                const double* b = d.bhat + (size_t)f * K3_Q + kx;
+                bh[p].x = __ldg(b);
+                bh[p].y = has1 ? __ldg(b + 1) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int f = fold256(t + 16 * j);
+                double2 v = make_double2(0.0, 0.0);
+                if (f < H) v = *reinterpret_cast<const double2*>(xs + f * K3_XS + kx);
+                re[j] = v.x; im[j] = v.y;
+            }
+            fft256_pass1(t, re, im, tw_s, xbuf);
+            __syncwarp(gmask);
+            fft256_pass2(t, re, im, xbuf);
+            __syncwarp(gmask);
+            double re2[16], im2[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {           // spectrum * beam, back to natural register order
+                re2[j] = re[rev16(j)] * bh[rev16(j)].x;
+                im2[j] = im[rev16(j)] * bh[rev16(j)].y;
+            }
+            fft256_pass1(t, re2, im2, tw_s, xbuf);
+            __syncwarp(gmask);
+            fft256_pass2(t, re2, im2, xbuf);
+            __syncwarp(gmask);
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const int u = t + 16 * rev16(p);
+                if (u < H) *reinterpret_cast<double2*>(xs + u * K3_XS + kx) = make_double2(re2[p], im2[p]);
+            }
+        }
+        __syncthreads();
+
+        // ================= phase C: rows back to pixel space, in place: xs[u, v] = conv_c[u, v]
+        for (int rp = grp; rp < npair; rp += K3_GROUPS) {
+            const int u0 = 2 * rp, u1 = u0 + 1;
+            const bool has1 = u1 < H;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int f = fold256(t + 16 * j);
+                re[j] = xs[u0 * K3_XS + f];
+                im[j] = has1 ? xs[u1 * K3_XS + f] : 0.0;
+            }
+            fft256_pass1(t, re, im, tw_s, xbuf);
+            __syncwarp(gmask);
+            fft256_pass2(t, re, im, xbuf);
+            __syncwarp(gmask);
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const int v = t + 16 * rev16(p);
+                if (v < hp16) {
+                    const bool in = v < H;
+                    xs[u0 * K3_XS + v] = in ? re[p] : 0.0;
+                    if (has1) xs[u1 * K3_XS + v] = in ? im[p] : 0.0;
+                }
+            }
+        }
+        __syncthreads();
+
+        if (a.convq) {
+            double* cq = a.convq + (size_t)w * H * H;
+            for (int i = tid; i < H * H; i += K3_THREADS) cq[i] = xs[(i / H) * K3_XS + (i % H)];
+        }
+
+        // ================= phase D: G[kx] = sum_u hf[u,kx] sum_v conv_c[u,v] w_v cos(2 pi kx v/N)   (DMMA)
+        {
+            const int ntile = hp8 >> 3;
+            const int nut0 = (ntile + 1) >> 1;
+            const int frow = lane >> 2, fk = lane & 3;
+            const int voff = (fk & 1) + 8 * (fk >> 1);          // k-permutation {0,1,8,9}: conflict-free fragments
+            for (int item = warp; item < 2 * ntile; item += K3_THREADS / 32) {
+                const int jt = item % ntile, half = item / ntile;
+                const int ut_lo = half ? nut0 : 0, ut_hi = half ? ntile : nut0;
+                const int nut = ut_hi - ut_lo;
+                const int kx = jt * 8 + frow;                    // B-fragment column of this lane
+                double acc[K3_MAXUT][2];
+#pragma unroll
+                for (int i = 0; i < K3_MAXUT; ++i) acc[i][0] = acc[i][1] = 0.0;
+                const double* arow = xs + (size_t)(ut_lo * 8 + frow) * K3_XS + voff;
+                for (int ks = 0; ks < (hp16 >> 2); ++ks) {
+                    const int v = 16 * (ks >> 2) + 2 * (ks & 3) + voff;
+                    double b = 0.0;
+                    if (kx < H && v < H) b = costab_s[(kx * v) % N] * (v ? 2.0 : 1.0);
+                    const double* ap = arow + 16 * (ks >> 2) + 2 * (ks & 3);
+#pragma unroll
+                    for (int i = 0; i < K3_MAXUT; ++i)
+                        if (i < nut) dmma884(acc[i][0], acc[i][1], ap[(size_t)i * 8 * K3_XS], b);
+                }
+                // fold in hf[u, kx] and reduce over the 8 fragment rows
+                double g0 = 0.0, g1 = 0.0;
+                const int kc = jt * 8 + 2 * fk;
+#pragma unroll
+                for (int i = 0; i < K3_MAXUT; ++i)
+                    if (i < nut) {
+                        const double2 h = __ldg(reinterpret_cast<const double2*>(
+                            d.hf_pad + (size_t)((ut_lo + i) * 8 + frow) * hp8 + kc));
+                        g0 += acc[i][0] * h.x;
+                        g1 += acc[i][1] * h.y;
+                    }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    g0 += __shfl_xor_sync(0xffffffffu, g0, o);
+                    g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+                }
+                if (lane < 4) {
+                    gpart_s[half * hp8 + kc] = g0;
+                    gpart_s[half * hp8 + kc + 1] = g1;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ================= phase E: row[v] = 1/N^2 sum_kx w_kx cos(2 pi kx v / N) G[kx]
+        for (int idx = tid; idx < 2 * H; idx += K3_THREADS) {
+            const int v = idx % H, part = idx / H;
+            double s0 = 0.0, s1 = 0.0;
+            int m = (part * v) % N;                  // (kx * v) mod N, kx = part, part+2, ...
+            const int step = (2 * v) % N;
+            int kx = part;
+            for (; kx + 2 < H; kx += 4) {
+                double g = gpart_s[kx] + gpart_s[hp8 + kx];
+                s0 += costab_s[m] * (kx ? 2.0 : 1.0) * g;
+                m += step; if (m >= N) m -= N;
+                double g2 = gpart_s[kx + 2] + gpart_s[hp8 + kx + 2];
+                s1 += costab_s[m] * 2.0 * g2;
+                m += step; if (m >= N) m -= N;
+            }
+            for (; kx < H; kx += 2) {
+                double g = gpart_s[kx] + gpart_s[hp8 + kx];
+                s0 += costab_s[m] * (kx ? 2.0 : 1.0) * g;
+                m += step; if (m >= N) m -= N;
+            }
+            outp_s[part * hp8 + v] = s0 + s1;
+        }
+        // h(0) = w_t0 . t_prof  (warp 7 while the others finish phase E)
+        if (warp == 7) {
+            double s = 0.0;
+            for (int i = lane; i < d.nt; i += 32) s += __ldg(d.w_t0 + i) * tsz_s[i];
+            s = warp_sum(s);
+            if (lane == 0) tarr_s[0] = s;
+        }
+        for (int i = tid; i < d.nt; i += K3_THREADS) tarr_s[i + 1] = tsz_s[i];
+        __syncthreads();
+
+        // ================= phase F: brightness profile, model at the data radii, chi^2, total
+        const int csrc = d.slot_src[JX_CALIB];
+        const double calib = csrc < 0 ? d.slot_val[JX_CALIB] : a.theta[(size_t)w * d.ndim + csrc];
+        const double inv_n2 = 1.0 / ((double)N * (double)N);
+        for (int v = tid; v < H; v += K3_THREADS) {
+            const double r = (outp_s[v] + outp_s[hp8 + v]) * inv_n2;
+            out_s[v] = r;
+            const double br = r * linear_extrap(tarr_s[v], d.conv_T, d.conv_I, d.nconv) * calib;
+            bright_s[v] = br;
+            if (a.row) a.row[(size_t)w * H + v] = r;
+            if (a.bright) a.bright[(size_t)w * H + v] = br;
+        }
+        __syncthreads();
+        for (int dpt = warp; dpt < d.nd; dpt += K3_THREADS / 32) {
+            double s = 0.0;
+            const double* g = d.g_op + (size_t)dpt * H;
+            for (int i = lane; i < H; i += 32) s += __ldg(g + i) * bright_s[i];
+            s = warp_sum(s);
+            if (lane == 0) {
+                model_s[dpt] = s;
+                if (a.model) a.model[(size_t)w * d.nd + dpt] = s;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double c = 0.0;
+            for (int i = lane; i < d.nd; i += 32) {
+                double z = (__ldg(d.flux + i) - model_s[i]) / __ldg(d.flux_err + i);
+                z = z * z;
+                if (z == z) c += z;                 // np.nansum drops NaN terms
+            }
+            c = warp_sum(c);
+            if (lane == 0) {
+                if (a.chisq) a.chisq[w] = c;
+                if (a.ll) {
+                    const double xl = a.xlike ? a.xlike[w] : 0.0;
+                    const double pr = a.prior ? a.prior[w] : 0.0;
+                    a.ll[w] = (xl + pr) + (-c / 2.0);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- parity taps (not on the production path) -------------------------------------------------
+
+// y_2d[w, y, x] = spline at d_mat[y, x]: quarter-plane pixel (|y-c|, |x-c|)
+__global__ void k3_tap_y2d_kernel(jx_dev d, const double* coef, int W, double* y2d) {
+    const int w = blockIdx.y;
+    const int N = d.nmap, c = N / 2, H = d.nh;
+    const double* cf = coef + (size_t)w * d.ncoef;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * N; i += gridDim.x * blockDim.x) {
+        int y = i / N, x = i % N;
+        int u = y < c ? c - y : y - c, v = x < c ? c - x : x - c;
+        y2d[(size_t)w * N * N + i] = spline_pixel(cf, d.nseg, d.seg16, d.dx, u * H + v);
+    }
+}
+
+__global__ void k3_tap_expand_kernel(jx_dev d, const double* convq, int W, double* full) {
+    const int w = blockIdx.y;
+    const int N = d.nmap, c = N / 2, H = d.nh;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * N; i += gridDim.x * blockDim.x) {
+        int y = i / N, x = i % N;
+        int u = y < c ? c - y : y - c, v = x < c ? c - x : x - c;
+        full[(size_t)w * N * N + i] = convq[(size_t)w * H * H + u * H + v];
+    }
+}
+
+// map_out quarter plane by dense cosine transforms (tap only; O(H^3) per walker, one CTA per walker):
+//   Chat = Cw conv Cw^T,  F = Chat * filt,  out = 1/N^2 Cw^T-style inverse on both axes
+__global__ void k3_tap_mapout_kernel(jx_dev d, const double* costab, const double* convq, int W, double* mapout,
+                                     double* scratch) {
+    const int w = blockIdx.x;
+    const int N = d.nmap, c = N / 2, H = d.nh;
+    const double* cq = convq + (size_t)w * H * H;
+    double* s1 = scratch + (size_t)w * 2 * H * H;
+    double* s2 = s1 + (size_t)H * H;
+    // s1[u, kx] = sum_v conv[u,v] w_v cos(kx v)
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
+        int u = i / H, kx = i % H;
+        double s = 0.0;
+        for (int v = 0; v < H; ++v) s += cq[u * H + v] * (v ? 2.0 : 1.0) * costab[(kx * v) % N];
+        s1[i] = s;
+    }
+    __syncthreads();
+    // s2[ky, kx] = filt[ky,kx] * sum_u w_u cos(ky u) s1[u, kx]
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
+        int ky = i / H, kx = i % H;
+        double s = 0.0;
+        for (int u = 0; u < H; ++u) s += s1[u * H + kx] * (u ? 2.0 : 1.0) * costab[(ky * u) % N];
+        s2[i] = s * d.filt_q[i];
+    }
+    __syncthreads();
+    // s1[ky, v] = sum_kx w_kx cos(kx v) s2[ky, kx]
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
+        int ky = i / H, v = i % H;
+        double s = 0.0;
+        for (int kx = 0; kx < H; ++kx) s += s2[ky * H + kx] * (kx ? 2.0 : 1.0) * costab[(kx * v) % N];
+        s1[i] = s;
+    }
+    __syncthreads();
+    // s2[u, v] = 1/N^2 sum_ky w_ky cos(ky u) s1[ky, v]
+    const double inv = 1.0 / ((double)N * (double)N);
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
+        int u = i / H, v = i % H;
+        double s = 0.0;
+        for (int ky = 0; ky < H; ++ky) s += s1[ky * H + v] * (ky ? 2.0 : 1.0) * costab[(ky * u) % N];
+        s2[i] = s * inv;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N * N; i += blockDim.x) {
+        int y = i / N, x = i % N;
+        int u = y < c ? c - y : y - c, v = x < c ? c - x : x - c;
+        mapout[(size_t)w * N * N + i] = s2[u * H + v];
+    }
+}
+
+}  // namespace
+
+cudaError_t jx_szmap_configure(const jx_dev& d) {
+    k3_smem_layout L = k3_layout(d, d.hp8);
+    return cudaFuncSetAttribute(k3_szmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+}
+
+size_t jx_szmap_smem_bytes(const jx_dev& d) { return k3_layout(d, d.hp8).total; }
+
+cudaError_t jx_launch_szmap(const jx_dev& d, const double* theta, const double* coef, const double* tsz,
+                            const uint32_t* flags, const double* prior, const double* xlike, int W, int sm_count,
+                            double* convq, double* row, double* bright, double* model, double* chisq, double* ll,
+                            cudaStream_t st) {
+    if (W <= 0) return cudaSuccess;
+    k3_args a;
+    a.d = d; a.theta = theta; a.coef = coef; a.tsz = tsz; a.prior = prior; a.xlike = xlike; a.flags = flags;
+    a.W = W;
+    a.convq = convq; a.row = row; a.bright = bright; a.model = model; a.chisq = chisq; a.ll = ll;
+    k3_smem_layout L = k3_layout(d, d.hp8);
+    int grid = W < sm_count ? W : sm_count;
+    k3_szmap_kernel<<<grid, K3_THREADS, L.total, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t jx_launch_tap_y2d(const jx_dev& d, const double* coef, int W, double* y2d, cudaStream_t st) {
+    for (int w0 = 0; w0 < W; w0 += 32768) {
+        int wc = W - w0 < 32768 ? W - w0 : 32768;
+        dim3 grid(32, wc);
+        k3_tap_y2d_kernel<<<grid, 256, 0, st>>>(d, coef + (size_t)w0 * d.ncoef, wc,
+                                                 y2d + (size_t)w0 * d.nmap * d.nmap);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t jx_launch_tap_expand(const jx_dev& d, const double* convq, int W, double* conv2d, cudaStream_t st) {
+    for (int w0 = 0; w0 < W; w0 += 32768) {
+        int wc = W - w0 < 32768 ? W - w0 : 32768;
+        dim3 grid(32, wc);
+        k3_tap_expand_kernel<<<grid, 256, 0, st>>>(d, convq + (size_t)w0 * d.nh * d.nh, wc,
+                                                    conv2d + (size_t)w0 * d.nmap * d.nmap);
+    }
+    return cudaGetLastError();
+}
+
+// scratch: [W, 2, H, H] doubles owned by the caller
+cudaError_t jx_launch_tap_mapout(const jx_dev& d, const double* convq, int W, double* mapout, double* scratch,
+                                 cudaStream_t st) {
+    k3_tap_mapout_kernel<<<W, 256, 0, st>>>(d, d.costab, convq, W, mapout, scratch);
+    return cudaGetLastError();
+}

@@ -1,0 +1,109 @@
+// K4 -- X-ray band emissivity from the cooling-function tables, annulus projection and the Cash
+// statistic, one warp per walker.
+//
+// Replaces Fit.calcProfiles -> Band.calcProjProfile -> CountRate.getCountRate (mbproj2; call site
+// joxsz_funcs.py:527), the positivity gate (:529-532) and mylikeFromProfs / cashLogLikelihood (:495-505):
+//
+//   lnT    = ln(clip(T_X, Tmin, Tmax))
+//   rate_s = (exp(interp(lnT, Tlog, t0)) + (exp(interp(lnT, Tlog, t1)) - exp(interp(lnT, Tlog, t0))) * Z) * ne^2
+//   pred_j = (sum_s projvols[j, s] rate_s) * areascale_j * exposure_j + bkg_j * backscale
+//   like   = sum_bands [ sum_j cts_j ln pred_j - sum_j pred_j ]   over bins with cts_j not NaN
+//
+// Lane a owns shell a for the emissivity and annulus a for the projection; the per-walker rate vector
+// goes through shared memory.  Tables (2 x nb x ntab doubles) and projvols are read through the
+// read-only path and stay L1/L2 resident (every warp reads the same 16 KB).
+#include "jx_common.cuh"
+
+namespace {
+
+constexpr int K4_WARPS = 8;
+
+struct k4_args {
+    jx_dev d;
+    const double *theta, *ne_ann, *tx_ann;
+    int W;
+    double *pred, *cash;
+    uint32_t* flags;
+};
+
+// numpy.interp for one abscissa on an increasing grid: clamps outside, NaN propagates
+JX_D double np_interp(double x, const double* __restrict__ xp, const double* __restrict__ fp, int n) {
+    if (x != x) return x;
+    if (x > __ldg(xp + n - 1)) return __ldg(fp + n - 1);
+    if (x < __ldg(xp)) return __ldg(fp);
+    if (x == __ldg(xp + n - 1)) return __ldg(fp + n - 1);
+    int lo = 0, hi = n - 1;          // invariant: xp[lo] <= x < xp[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (x >= __ldg(xp + mid)) lo = mid; else hi = mid;
+    }
+    double x0 = __ldg(xp + lo), f0 = __ldg(fp + lo);
+    double slope = (__ldg(fp + lo + 1) - f0) / (__ldg(xp + lo + 1) - x0);
+    return slope * (x - x0) + f0;
+}
+
+__global__ void __launch_bounds__(K4_WARPS * 32) k4_xray_kernel(const __grid_constant__ k4_args a) {
+    extern __shared__ double k4_smem[];
+    const jx_dev& d = a.d;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * K4_WARPS + warp;
+    if (w >= a.W) return;
+    double* rate_s = k4_smem + (size_t)warp * d.na;
+
+    const int zsrc = d.slot_src[JX_ZMET], bsrc = d.slot_src[JX_BACKSCALE];
+    const double Z = zsrc < 0 ? d.slot_val[JX_ZMET] : a.theta[(size_t)w * d.ndim + zsrc];
+    const double backscale = bsrc < 0 ? d.slot_val[JX_BACKSCALE] : a.theta[(size_t)w * d.ndim + bsrc];
+
+    double like = 0.0;
+    bool nonpos = false;
+    // one lane per shell/annulus: na <= 32 is enforced by jx_create
+    const int s = lane;                 // shell / annulus index of this lane
+    double ne = 0.0, lnT = 0.0;
+    if (s < d.na) {
+        ne = a.ne_ann[(size_t)w * d.na + s];
+        double T = a.tx_ann[(size_t)w * d.na + s];
+        // np.clip propagates NaN
+        double Tc = (T != T) ? T : fmin(fmax(T, d.tmin), d.tmax);
+        lnT = log(Tc);
+    }
+    for (int b = 0; b < d.nb; ++b) {
+        if (s < d.na) {
+            double r0 = exp(np_interp(lnT, d.tlog, d.lnrate0 + (size_t)b * d.ntab, d.ntab));
+            double r1 = exp(np_interp(lnT, d.tlog, d.lnrate1 + (size_t)b * d.ntab, d.ntab));
+            rate_s[s] = (r0 + (r1 - r0) * Z) * (ne * ne);
+        }
+        __syncwarp();
+        double t1 = 0.0, t2 = 0.0;
+        if (s < d.na) {
+            const double* pv = d.projvols + (size_t)s * d.na;
+            double proj = 0.0;
+            for (int k = 0; k < d.na; ++k) proj += __ldg(pv + k) * rate_s[k];
+            size_t o = (size_t)b * d.na + s;
+            double pred = proj * __ldg(d.srcscale + o) + __ldg(d.bkgterm + o) * backscale;
+            if (a.pred) a.pred[((size_t)w * d.nb + b) * d.na + s] = pred;
+            if (!(pred > 0.0)) nonpos = true;
+            double c = __ldg(d.cts + o);
+            if (c == c) { t1 = c * log(pred); t2 = pred; }
+        }
+        __syncwarp();
+        double lb = warp_sum(t1) - warp_sum(t2);
+        like += isfinite(lb) ? lb : jx_neg_inf();
+    }
+    nonpos = __any_sync(0xffffffffu, nonpos);
+    if (lane == 0) {
+        if (a.cash) a.cash[w] = nonpos ? jx_neg_inf() : like;
+        if (a.flags && nonpos) a.flags[w] |= JX_FLAG_XNONPOS;
+    }
+}
+
+}  // namespace
+
+cudaError_t jx_launch_xray(const jx_dev& d, const double* theta, const double* ne_ann, const double* tx_ann,
+                           int W, double* pred, double* cash, uint32_t* flags, cudaStream_t st) {
+    if (W <= 0) return cudaSuccess;
+    k4_args a{d, theta, ne_ann, tx_ann, W, pred, cash, flags};
+    size_t smem = (size_t)K4_WARPS * d.na * sizeof(double);
+    int blocks = (W + K4_WARPS - 1) / K4_WARPS;
+    k4_xray_kernel<<<blocks, K4_WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}

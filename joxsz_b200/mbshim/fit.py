@@ -1,0 +1,54 @@
+"""``mbproj2.Fit`` work-alike: parameter bookkeeping, X-ray profile prediction, simplex refit."""
+import numpy as np
+
+debugfit = True
+
+
+class Fit:
+    def __init__(self, pars, model, data):
+        self.pars = pars
+        self.model = model
+        self.data = data
+        self.refreshThawed()
+        self.bestlike = -1e99
+
+    def refreshThawed(self):
+        self.thawed = [name for name, par in sorted(self.pars.items()) if not par.frozen]
+
+    def thawedParVals(self):
+        return [self.pars[name].val for name in self.thawed]
+
+    def updateThawed(self, vals):
+        for val, name in zip(vals, self.thawed):
+            self.pars[name].val = val
+
+    def calcProfiles(self):
+        ne_prof, T_prof, Z_prof = self.model.computeProfs(self.pars)
+        return [band.calcProjProfile(self.data.annuli, ne_prof, T_prof, Z_prof,
+                                     self.model.NH_1022pcm2, backscale=self.pars["backscale"].val)
+                for band in self.data.bands]
+
+    def getLikelihood(self, vals=None):
+        raise NotImplementedError("bind joxsz_funcs.getLikelihood (joxsz_main.py:187)")
+
+    def doFitting(self, silent=False, maxiter=10):
+        """Alternate Nelder-Mead / Powell on -getLikelihood until it improves by < 0.1."""
+        from scipy import optimize
+
+        def neg(vals):
+            like = self.getLikelihood(vals)
+            return -like if np.isfinite(like) else 1e99
+
+        like = self.getLikelihood(self.thawedParVals())
+        for _ in range(maxiter):
+            for method in ("Nelder-Mead", "Powell"):
+                res = optimize.minimize(neg, np.array(self.thawedParVals(), dtype=float), method=method)
+                self.updateThawed(np.atleast_1d(res.x))
+            newlike = self.getLikelihood(self.thawedParVals())
+            if not silent:
+                print("Fit: %g -> %g" % (like, newlike))
+            done = abs(newlike - like) < 0.1
+            like = newlike
+            if done:
+                break
+        return like
