@@ -167,6 +167,11 @@ int jx_sz_profile(jx_handle* h, const double* theta, int32_t W,
  * (`mylikeFromProfs`, :495-505; -inf where a profile is not > 0, :529-532) [W]. */
 int jx_xray(jx_handle* h, const double* theta, int32_t W, double* pred, double* cash, void* stream);
 
+/* `mylikeFromProfs` on caller-supplied predicted profiles (joxsz_funcs.py:495-505): pred [W,nb,na] ->
+ * cash [W] = sum over bands of cashLogLikelihood over bins whose counts are not NaN (-inf if a band's
+ * sum is not finite).  No positivity gate: that is the caller's `if` at :529-532. */
+int jx_cash_from_profiles(jx_handle* h, const double* pred, int32_t W, double* cash, void* stream);
+
 /* Component methods at arbitrary radii (press_fun :275, press_derivative :289, vikhFunction :375,
  * temp_fun :321, mass_fun :428).  No handle: `pars` [W, JX_NPAR] holds full parameter vectors.
  * Outputs [W, n] each, NULL to skip. */
@@ -175,24 +180,31 @@ int jx_radial_profiles(const double* pars, int32_t W, int32_t dens_mode, const d
                        double* mass, int32_t device, void* stream);
 
 /* ---- ensemble stretch move (emcee RedBlueMove/StretchMove semantics; joxsz_main.py:206-210).
- * The ensemble has `nall` walkers; `coords` [nall, ndim] is the gathered ensemble (identical on every
- * rank); walkers [first, first+count) are local to this rank.  `perm` [nall] is a random permutation of
- * 0..nall-1 shared by all ranks and `pos` [nall] its inverse; the colour of walker i is pos[i] & 1
- * (emcee: `inds = arange(n) % 2; shuffle(inds)`).  For each local walker of colour `split`: partner
- * j = perm[2 r + (1 - split)] with r uniform over the other colour, z = ((a-1) u + 1)^2 / a,
- * prop = c_j - (c_j - s) z, factor = (ndim-1) ln z, active = 1.  Walkers of the other colour get their
- * current position, factor 0 and active = 0.  RNG: Philox4x32-10, key = seed, counter = (global
- * walker index, iteration, split, purpose), so draws do not depend on how walkers are sharded. */
-int jx_stretch_propose(const double* coords, const int32_t* perm, const int32_t* pos, int32_t nall, int32_t ndim,
-                       int32_t first, int32_t count, int32_t split, double a, uint64_t seed, uint64_t iteration,
-                       double* prop /*[count,ndim]*/, double* factor /*[count]*/, int32_t* active /*[count]*/,
-                       int32_t device, void* stream);
-/* Accept where active and factor + lp_new - lp_old > ln(u): copies prop/lp_new over coords_local
- * [count, ndim] / lp_local [count] and increments naccept [count] (emcee RedBlueMove.propose). */
-int jx_stretch_accept(double* coords_local, double* lp_local, const double* prop, const double* lp_new,
-                      const double* factor, const int32_t* active, int32_t ndim, int32_t first, int32_t count,
-                      int32_t split, uint64_t seed, uint64_t iteration, int32_t* naccept, int32_t device,
-                      void* stream);
+ * Every rank holds the whole ensemble `coords` [nall, ndim], `lp` [nall] (kept identical by the
+ * all-gather of each half-step's results).  `perm` [nall] is a random permutation of 0..nall-1 shared
+ * by all ranks; the colour of the walker at position p of `perm` is p & 1 (emcee:
+ * `inds = arange(n) % 2; shuffle(inds)`).  In the half-step `split` the active walkers are
+ * perm[2 r + split], r = 0..ns-1 with ns = (nall - split + 1) / 2; a rank processes the contiguous slice
+ * r in [r_first, r_first + r_count) -- equal, fixed-size work per rank whatever the colouring.
+ * RNG: Philox4x32-10, key = seed, counter = (walker index, iteration, split | purpose): a chain does
+ * not depend on the number of ranks.
+ *
+ * propose: partner j = perm[2 rint + (1 - split)], rint uniform over the other colour;
+ *          z = ((a-1) u + 1)^2 / a;  prop = c_j - (c_j - x_k) z;  factor = (ndim - 1) ln z. */
+int jx_stretch_propose(const double* coords, const int32_t* perm, int32_t nall, int32_t ndim, int32_t split,
+                       int32_t r_first, int32_t r_count, double a, uint64_t seed, uint64_t iteration,
+                       double* prop /*[r_count,ndim]*/, double* factor /*[r_count]*/, int32_t device, void* stream);
+/* accept: packed[i] = (new position [ndim], new log-prob, accepted 0/1) for slice entry i, where the
+ * move is accepted iff factor + lp_new - lp[k] > ln(u) (emcee RedBlueMove.propose). */
+int jx_stretch_accept(const double* coords, const double* lp, const int32_t* perm, int32_t nall, int32_t ndim,
+                      int32_t split, int32_t r_first, int32_t r_count, const double* prop, const double* lp_new,
+                      const double* factor, uint64_t seed, uint64_t iteration,
+                      double* packed /*[r_count, ndim+2]*/, int32_t device, void* stream);
+/* scatter: write the gathered results of all ranks, packed_all [>= ns, ndim+2] in r order, back into
+ * coords / lp and add the acceptance flags to naccept [nall]. */
+int jx_stretch_scatter(double* coords, double* lp, int32_t* naccept, const int32_t* perm, int32_t nall,
+                       int32_t ndim, int32_t split, const double* packed_all, int32_t ns, int32_t device,
+                       void* stream);
 
 /* ---- measurement helpers (bench.py) */
 enum jx_stage { JX_ST_PROFILES = 0, JX_ST_PROJECT, JX_ST_SZMAP, JX_ST_XRAY, JX_NSTAGE };

@@ -1,0 +1,196 @@
+"""BatchedLikelihood: the JoXSZ joint log-likelihood for every walker at once, on one B200.
+
+``BatchedLikelihood(fit)(theta[W, ndim]) -> ll[W]`` is what an ensemble sampler calls once per
+half-step (emcee ``vectorize=True`` convention) in place of ``W`` calls of the reference's
+``getLikelihood`` (``joxsz_funcs.py:507-546``).  PyTorch only owns buffers and the stream; all
+arithmetic happens in libjoxsz_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .packer import PackedSetup
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+
+
+class BatchedLikelihood:
+    def __init__(self, fit=None, packed: PackedSetup | None = None, max_walkers=1024, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.JxError("BatchedLikelihood needs a CUDA device: the likelihood has no CPU implementation")
+        self.lib = _lib.load()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", int(device) if not isinstance(device, torch.device) else device.index or 0)
+        if packed is None:
+            packed = PackedSetup(fit, max_walkers=max_walkers, device=self.device.index)
+        else:
+            packed.device = self.device.index
+            packed.max_walkers = max(int(max_walkers), 1) if max_walkers else packed.max_walkers
+            packed._struct = None
+        self.packed = packed
+        self.ndim = packed.ndim
+        self.max_walkers = packed.max_walkers
+        handle = C.c_void_p()
+        rc = self.lib.jx_create(C.byref(packed.struct()), C.byref(handle))
+        _lib.check(rc, None)
+        self._h = handle
+        self._pinned_in = None
+        self._pinned_out = None
+
+    # ------------------------------------------------------------------ life cycle
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.jx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _theta_dev(self, theta):
+        """[W, ndim] float64 CUDA tensor from numpy / torch input (host input goes through pinned memory)."""
+        if isinstance(theta, torch.Tensor):
+            t = theta
+            if t.dim() == 1:
+                t = t.unsqueeze(0)
+            if t.device != self.device or t.dtype != torch.float64 or not t.is_contiguous():
+                t = t.to(device=self.device, dtype=torch.float64).contiguous()
+            return t
+        a = np.ascontiguousarray(np.atleast_2d(np.asarray(theta, dtype=np.float64)))
+        W = a.shape[0]
+        if self._pinned_in is None or self._pinned_in.shape[0] < W:
+            self._pinned_in = torch.empty((max(W, 1), self.ndim), dtype=torch.float64).pin_memory()
+        self._pinned_in[:W].copy_(torch.from_numpy(a))
+        return self._pinned_in[:W].to(self.device, non_blocking=True)
+
+    def _check_theta(self, t):
+        if t.dim() != 2 or t.shape[1] != self.ndim:
+            raise ValueError(f"theta must be [W, {self.ndim}], got {tuple(t.shape)}")
+        if t.shape[0] > self.max_walkers:
+            raise ValueError(f"W={t.shape[0]} exceeds max_walkers={self.max_walkers}")
+
+    def _new(self, *shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    # ------------------------------------------------------------------ hot path
+    def loglike_device(self, theta_dev: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """theta_dev [W, ndim] CUDA float64 -> ll [W] CUDA float64, asynchronous on the current stream."""
+        self._check_theta(theta_dev)
+        W = theta_dev.shape[0]
+        if out is None:
+            out = self._new(W)
+        with torch.cuda.device(self.device):
+            rc = self.lib.jx_loglike(self._h, _ptr(theta_dev), W, _ptr(out), self._stream())
+        _lib.check(rc, self._h)
+        return out
+
+    def __call__(self, theta):
+        """numpy/torch [W, ndim] (or [ndim]) -> same kind of array [W] (or a float)."""
+        single = (np.ndim(theta) == 1) if not isinstance(theta, torch.Tensor) else theta.dim() == 1
+        was_torch = isinstance(theta, torch.Tensor)
+        t = self._theta_dev(theta)
+        ll = self.loglike_device(t)
+        if was_torch and theta.is_cuda:
+            return ll[0] if single else ll
+        W = ll.shape[0]
+        if self._pinned_out is None or self._pinned_out.shape[0] < W:
+            self._pinned_out = torch.empty(max(W, 1), dtype=torch.float64).pin_memory()
+        self._pinned_out[:W].copy_(ll, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        res = self._pinned_out[:W].numpy().copy()
+        if was_torch:
+            res = torch.from_numpy(res)
+        return float(res[0]) if single else res
+
+    # ------------------------------------------------------------------ parity taps
+    def profiles(self, theta):
+        """K1: dict(pp [W,nr], tsz [W,sep], ne_ann, tx_ann [W,na], flags [W], prior [W]) as numpy."""
+        t = self._theta_dev(theta); self._check_theta(t)
+        W, p = t.shape[0], self.packed
+        o = dict(pp=self._new(W, p.nr), tsz=self._new(W, p.sep), ne_ann=self._new(W, p.na),
+                 tx_ann=self._new(W, p.na), flags=self._new(W, dtype=torch.int32), prior=self._new(W))
+        with torch.cuda.device(self.device):
+            rc = self.lib.jx_profiles(self._h, _ptr(t), W, _ptr(o["pp"]), _ptr(o["tsz"]), _ptr(o["ne_ann"]),
+                                      _ptr(o["tx_ann"]), _ptr(o["flags"]), _ptr(o["prior"]), self._stream())
+        _lib.check(rc, self._h)
+        return {k: v.cpu().numpy() for k, v in o.items()}
+
+    def sz_project(self, theta):
+        """K2: dict(y [W,nr], coef [W,4,nseg])."""
+        t = self._theta_dev(theta); self._check_theta(t)
+        W, p = t.shape[0], self.packed
+        y, coef = self._new(W, p.nr), self._new(W, 4 * p.map_ops.nseg)
+        with torch.cuda.device(self.device):
+            rc = self.lib.jx_sz_project(self._h, _ptr(t), W, _ptr(y), _ptr(coef), self._stream())
+        _lib.check(rc, self._h)
+        return dict(y=y.cpu().numpy(), coef=coef.cpu().numpy().reshape(W, 4, -1))
+
+    def sz_maps(self, theta, want=("y_2d", "conv_2d", "map_out")):
+        """K3 full maps [W,N,N] (reference joxsz_funcs.py:462-467)."""
+        t = self._theta_dev(theta); self._check_theta(t)
+        W, N = t.shape[0], self.packed.N
+        bufs = {k: (self._new(W, N, N) if k in want else None) for k in ("y_2d", "conv_2d", "map_out")}
+        with torch.cuda.device(self.device):
+            rc = self.lib.jx_sz_maps(self._h, _ptr(t), W, _ptr(bufs["y_2d"]), _ptr(bufs["conv_2d"]),
+                                     _ptr(bufs["map_out"]), self._stream())
+        _lib.check(rc, self._h)
+        return {k: v.cpu().numpy() for k, v in bufs.items() if v is not None}
+
+    def sz_profile(self, theta):
+        """K3+K5: dict(row, bright [W,H], model [W,Nd], chisq [W])."""
+        t = self._theta_dev(theta); self._check_theta(t)
+        W, p = t.shape[0], self.packed
+        o = dict(row=self._new(W, p.H), bright=self._new(W, p.H), model=self._new(W, p.flux.size),
+                 chisq=self._new(W))
+        with torch.cuda.device(self.device):
+            rc = self.lib.jx_sz_profile(self._h, _ptr(t), W, _ptr(o["row"]), _ptr(o["bright"]), _ptr(o["model"]),
+                                        _ptr(o["chisq"]), self._stream())
+        _lib.check(rc, self._h)
+        return {k: v.cpu().numpy() for k, v in o.items()}
+
+    def xray(self, theta):
+        """K4: dict(pred [W,nb,na], cash [W])."""
+        t = self._theta_dev(theta); self._check_theta(t)
+        W, p = t.shape[0], self.packed
+        pred, cash = self._new(W, p.nb, p.na), self._new(W)
+        with torch.cuda.device(self.device):
+            rc = self.lib.jx_xray(self._h, _ptr(t), W, _ptr(pred), _ptr(cash), self._stream())
+        _lib.check(rc, self._h)
+        return dict(pred=pred.cpu().numpy(), cash=cash.cpu().numpy())
+
+    def cash_from_profiles(self, pred):
+        """``mylikeFromProfs`` on given predicted profiles [W, nb, na] -> [W] (numpy)."""
+        p = self.packed
+        a = np.ascontiguousarray(np.asarray(pred, dtype=np.float64)).reshape(-1, p.nb, p.na)
+        if a.shape[0] > self.max_walkers:
+            raise ValueError(f"W={a.shape[0]} exceeds max_walkers={self.max_walkers}")
+        d = torch.from_numpy(a).to(self.device)
+        out = self._new(a.shape[0])
+        with torch.cuda.device(self.device):
+            rc = self.lib.jx_cash_from_profiles(self._h, _ptr(d), a.shape[0], _ptr(out), self._stream())
+        _lib.check(rc, self._h)
+        return out.cpu().numpy()
+
+    # ------------------------------------------------------------------ measurement
+    def set_profiling(self, on: bool):
+        _lib.check(self.lib.jx_set_profiling(self._h, int(bool(on))), self._h)
+
+    def stage_times(self):
+        """{stage: (total_ms, launches)} since the last call; resets the counters."""
+        ms = (C.c_double * _lib.JX_NSTAGE)()
+        n = (C.c_int64 * _lib.JX_NSTAGE)()
+        _lib.check(self.lib.jx_stage_times(self._h, ms, n), self._h)
+        return {name: (ms[i], n[i]) for i, name in enumerate(_lib.STAGE_NAMES)}

@@ -384,6 +384,14 @@ extern "C" int jx_xray(jx_handle* h, const double* theta, int32_t W, double* pre
     return JX_OK;
 }
 
+extern "C" int jx_cash_from_profiles(jx_handle* h, const double* pred, int32_t W, double* cash, void* stream) {
+    int rc = check_ready(h, pred, W);
+    if (rc) return rc;
+    if (!cash) return fail(h, JX_ERR_INVALID, "cash is NULL");
+    JX_CUDA(h, jx_launch_cash(h->d, pred, W, cash, (cudaStream_t)stream));
+    return JX_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // measurement helpers
 // ------------------------------------------------------------------------------------------------

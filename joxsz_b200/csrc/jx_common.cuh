@@ -95,6 +95,7 @@ cudaError_t jx_launch_project(const jx_dev& d, const double* pp, int W, const do
                               double* out, cudaStream_t st);
 cudaError_t jx_launch_xray(const jx_dev& d, const double* theta, const double* ne_ann, const double* tx_ann,
                            int W, double* pred, double* cash, uint32_t* flags, cudaStream_t st);
+cudaError_t jx_launch_cash(const jx_dev& d, const double* pred, int W, double* cash, cudaStream_t st);
 // production map stage: coef -> filtered row (+ optional quarter-plane convolved map), and the tail.
 // `flags` may be NULL (evaluate every walker).  ll may be NULL (taps).
 cudaError_t jx_launch_szmap(const jx_dev& d, const double* theta, const double* coef, const double* tsz,

@@ -96,7 +96,32 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_xray_kernel(const __grid_con
     }
 }
 
+__global__ void __launch_bounds__(K4_WARPS * 32)
+k4_cash_kernel(jx_dev d, const double* __restrict__ pred, int W, double* __restrict__ cash) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * K4_WARPS + warp;
+    if (w >= W) return;
+    double like = 0.0;
+    for (int b = 0; b < d.nb; ++b) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int s = lane; s < d.na; s += 32) {
+            double c = __ldg(d.cts + (size_t)b * d.na + s);
+            double m = pred[((size_t)w * d.nb + b) * d.na + s];
+            if (c == c) { t1 += c * log(m); t2 += m; }
+        }
+        double lb = warp_sum(t1) - warp_sum(t2);
+        like += isfinite(lb) ? lb : jx_neg_inf();
+    }
+    if (lane == 0) cash[w] = like;
+}
+
 }  // namespace
+
+cudaError_t jx_launch_cash(const jx_dev& d, const double* pred, int W, double* cash, cudaStream_t st) {
+    if (W <= 0) return cudaSuccess;
+    k4_cash_kernel<<<(W + K4_WARPS - 1) / K4_WARPS, K4_WARPS * 32, 0, st>>>(d, pred, W, cash);
+    return cudaGetLastError();
+}
 
 cudaError_t jx_launch_xray(const jx_dev& d, const double* theta, const double* ne_ann, const double* tx_ann,
                            int W, double* pred, double* cash, uint32_t* flags, cudaStream_t st) {

@@ -35,80 +35,100 @@ JX_HD double u01(uint32_t hi, uint32_t lo) {       // 53-bit uniform in [0, 1)
 
 constexpr uint32_t PURPOSE_PROPOSE = 0u, PURPOSE_ACCEPT = 1u;
 
-__global__ void k6_propose_kernel(const double* __restrict__ coords, const int32_t* __restrict__ perm,
-                                  const int32_t* __restrict__ pos, int nall, int ndim, int first, int count,
-                                  int split, double a, uint64_t seed, uint64_t iteration, double* __restrict__ prop,
-                                  double* __restrict__ factor, int32_t* __restrict__ active) {
+__global__ void k6_propose_kernel(const double* __restrict__ coords, const int32_t* __restrict__ perm, int nall,
+                                  int ndim, int split, int r_first, int r_count, double a, uint64_t seed,
+                                  uint64_t iteration, double* __restrict__ prop, double* __restrict__ factor) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const int gi = first + i;
-    const double* s = coords + (size_t)gi * ndim;
-    double* q = prop + (size_t)i * ndim;
-    if ((pos[gi] & 1) != split) {
-        for (int k = 0; k < ndim; ++k) q[k] = s[k];
-        factor[i] = 0.0;
-        active[i] = 0;
-        return;
-    }
-    philox4 r = philox4x32_10((uint32_t)gi, (uint32_t)iteration, (uint32_t)(iteration >> 32),
+    if (i >= r_count) return;
+    const int k = perm[2 * (r_first + i) + split];
+    philox4 r = philox4x32_10((uint32_t)k, (uint32_t)iteration, (uint32_t)(iteration >> 32),
                               ((uint32_t)split << 1) | PURPOSE_PROPOSE, (uint32_t)seed, (uint32_t)(seed >> 32));
     const double u = u01(r.v[0], r.v[1]);
     const double root = (a - 1.0) * u + 1.0;
     const double z = root * root / a;
     const int other = 1 - split;
     const int nc = (nall - other + 1) / 2;                // positions of parity `other` in 0..nall-1
-    int rint = (int)(((uint64_t)r.v[2] * (uint64_t)nc) >> 32);
+    const int rint = (int)(((uint64_t)r.v[2] * (uint64_t)nc) >> 32);
+    const double* s = coords + (size_t)k * ndim;
     const double* c = coords + (size_t)perm[2 * rint + other] * ndim;
-    for (int k = 0; k < ndim; ++k) q[k] = c[k] - (c[k] - s[k]) * z;
+    double* q = prop + (size_t)i * ndim;
+    for (int d = 0; d < ndim; ++d) q[d] = c[d] - (c[d] - s[d]) * z;
     factor[i] = ((double)ndim - 1.0) * log(z);
-    active[i] = 1;
 }
 
-__global__ void k6_accept_kernel(double* __restrict__ coords_local, double* __restrict__ lp_local,
+__global__ void k6_accept_kernel(const double* __restrict__ coords, const double* __restrict__ lp,
+                                 const int32_t* __restrict__ perm, int ndim, int split, int r_first, int r_count,
                                  const double* __restrict__ prop, const double* __restrict__ lp_new,
-                                 const double* __restrict__ factor, const int32_t* __restrict__ active, int ndim,
-                                 int first, int count, int split, uint64_t seed, uint64_t iteration,
-                                 int32_t* __restrict__ naccept) {
+                                 const double* __restrict__ factor, uint64_t seed, uint64_t iteration,
+                                 double* __restrict__ packed) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count || !active[i]) return;
-    const int gi = first + i;
-    philox4 r = philox4x32_10((uint32_t)gi, (uint32_t)iteration, (uint32_t)(iteration >> 32),
+    if (i >= r_count) return;
+    const int k = perm[2 * (r_first + i) + split];
+    philox4 r = philox4x32_10((uint32_t)k, (uint32_t)iteration, (uint32_t)(iteration >> 32),
                               ((uint32_t)split << 1) | PURPOSE_ACCEPT, (uint32_t)seed, (uint32_t)(seed >> 32));
     const double lnu = log(u01(r.v[0], r.v[1]));
-    const double lnpdiff = factor[i] + lp_new[i] - lp_local[i];
-    if (lnpdiff > lnu) {
-        for (int k = 0; k < ndim; ++k) coords_local[(size_t)i * ndim + k] = prop[(size_t)i * ndim + k];
-        lp_local[i] = lp_new[i];
-        if (naccept) naccept[i] += 1;
-    }
+    const double lnpdiff = factor[i] + lp_new[i] - lp[k];
+    const bool acc = lnpdiff > lnu;
+    const double* src = acc ? prop + (size_t)i * ndim : coords + (size_t)k * ndim;
+    double* o = packed + (size_t)i * (ndim + 2);
+    for (int d = 0; d < ndim; ++d) o[d] = src[d];
+    o[ndim] = acc ? lp_new[i] : lp[k];
+    o[ndim + 1] = acc ? 1.0 : 0.0;
+}
+
+__global__ void k6_scatter_kernel(double* __restrict__ coords, double* __restrict__ lp, int32_t* __restrict__ naccept,
+                                  const int32_t* __restrict__ perm, int ndim, int split,
+                                  const double* __restrict__ packed_all, int ns) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= ns) return;
+    const int k = perm[2 * r + split];
+    const double* o = packed_all + (size_t)r * (ndim + 2);
+    for (int d = 0; d < ndim; ++d) coords[(size_t)k * ndim + d] = o[d];
+    lp[k] = o[ndim];
+    if (naccept && o[ndim + 1] != 0.0) naccept[k] += 1;
 }
 
 }  // namespace
 
-extern "C" int jx_stretch_propose(const double* coords, const int32_t* perm, const int32_t* pos, int32_t nall,
-                                  int32_t ndim, int32_t first, int32_t count, int32_t split, double a,
-                                  uint64_t seed, uint64_t iteration, double* prop, double* factor,
-                                  int32_t* active, int32_t device, void* stream) {
-    if (!coords || !perm || !pos || !prop || !factor || !active) return JX_ERR_INVALID;
-    if (nall < 2 || ndim < 1 || first < 0 || count < 0 || first + count > nall || (split != 0 && split != 1) ||
-        !(a > 1.0))
-        return JX_ERR_INVALID;
-    if (count == 0) return JX_OK;
+static bool slice_ok(int nall, int split, int r_first, int r_count) {
+    if (nall < 2 || (split != 0 && split != 1) || r_first < 0 || r_count < 0) return false;
+    const int ns = (nall - split + 1) / 2;
+    return r_first + r_count <= ns;
+}
+
+extern "C" int jx_stretch_propose(const double* coords, const int32_t* perm, int32_t nall, int32_t ndim,
+                                  int32_t split, int32_t r_first, int32_t r_count, double a, uint64_t seed,
+                                  uint64_t iteration, double* prop, double* factor, int32_t device, void* stream) {
+    if (!coords || !perm || !prop || !factor || ndim < 1 || !(a > 1.0)) return JX_ERR_INVALID;
+    if (!slice_ok(nall, split, r_first, r_count)) return JX_ERR_INVALID;
+    if (r_count == 0) return JX_OK;
     if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
-    k6_propose_kernel<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        coords, perm, pos, nall, ndim, first, count, split, a, seed, iteration, prop, factor, active);
+    k6_propose_kernel<<<(r_count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        coords, perm, nall, ndim, split, r_first, r_count, a, seed, iteration, prop, factor);
     return cudaGetLastError() == cudaSuccess ? JX_OK : JX_ERR_CUDA;
 }
 
-extern "C" int jx_stretch_accept(double* coords_local, double* lp_local, const double* prop, const double* lp_new,
-                                 const double* factor, const int32_t* active, int32_t ndim, int32_t first,
-                                 int32_t count, int32_t split, uint64_t seed, uint64_t iteration, int32_t* naccept,
-                                 int32_t device, void* stream) {
-    if (!coords_local || !lp_local || !prop || !lp_new || !factor || !active) return JX_ERR_INVALID;
-    if (ndim < 1 || first < 0 || count < 0 || (split != 0 && split != 1)) return JX_ERR_INVALID;
-    if (count == 0) return JX_OK;
+extern "C" int jx_stretch_accept(const double* coords, const double* lp, const int32_t* perm, int32_t nall,
+                                 int32_t ndim, int32_t split, int32_t r_first, int32_t r_count, const double* prop,
+                                 const double* lp_new, const double* factor, uint64_t seed, uint64_t iteration,
+                                 double* packed, int32_t device, void* stream) {
+    if (!coords || !lp || !perm || !prop || !lp_new || !factor || !packed || ndim < 1) return JX_ERR_INVALID;
+    if (!slice_ok(nall, split, r_first, r_count)) return JX_ERR_INVALID;
+    if (r_count == 0) return JX_OK;
     if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
-    k6_accept_kernel<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        coords_local, lp_local, prop, lp_new, factor, active, ndim, first, count, split, seed, iteration, naccept);
+    k6_accept_kernel<<<(r_count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        coords, lp, perm, ndim, split, r_first, r_count, prop, lp_new, factor, seed, iteration, packed);
+    return cudaGetLastError() == cudaSuccess ? JX_OK : JX_ERR_CUDA;
+}
+
+extern "C" int jx_stretch_scatter(double* coords, double* lp, int32_t* naccept, const int32_t* perm, int32_t nall,
+                                  int32_t ndim, int32_t split, const double* packed_all, int32_t ns, int32_t device,
+                                  void* stream) {
+    if (!coords || !lp || !perm || !packed_all || ndim < 1) return JX_ERR_INVALID;
+    if (!slice_ok(nall, split, 0, ns)) return JX_ERR_INVALID;
+    if (ns == 0) return JX_OK;
+    if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
+    k6_scatter_kernel<<<(ns + 127) / 128, 128, 0, (cudaStream_t)stream>>>(coords, lp, naccept, perm, ndim, split,
+                                                                            packed_all, ns);
     return cudaGetLastError() == cudaSuccess ? JX_OK : JX_ERR_CUDA;
 }

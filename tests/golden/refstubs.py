@@ -1,0 +1,81 @@
+"""Import the UNMODIFIED reference ``/root/reference/joxsz_funcs.py`` in this container.
+
+Its third-party imports that are not installable here are stubbed in ``sys.modules``:
+
+* ``astropy.io.fits``  -> a two-line adapter over ``joxsz_b200.fitsio`` (same ``open(f)[''].data[0]`` shape)
+* ``mbproj2``          -> ``joxsz_b200.mbshim`` (restated from memory)
+* ``abel.direct``      -> ``oracle.joxsz_oracle.pyabel_direct_forward`` (restated; Appendix A.1)
+* ``h5py``             -> empty module (only used by add_backend_attrs / addCountCache)
+* ``scipy.integrate.simps`` -> ``simpson`` (removed from scipy >= 1.14; only used when calc_integ=True)
+
+Consequence, stated wherever the golden vectors are used: they pin this repo's oracle against the
+reference's OWN code, not against PyAbel / mbproj2 themselves.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+REFERENCE_DIR = "/root/reference"
+
+
+def reference_available():
+    return os.path.exists(os.path.join(REFERENCE_DIR, "joxsz_funcs.py"))
+
+
+def _install_stubs():
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.abspath(os.path.join(here, "..", ".."))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from joxsz_b200 import fitsio, mbshim
+    from oracle import joxsz_oracle as orc
+
+    class _HDU:
+        def __init__(self, rows):
+            self.data = rows
+
+    class _HDUList:
+        def __init__(self, filename):
+            self._rows = fitsio.read_bintable(filename, ext=1)
+
+        def __getitem__(self, key):
+            return _HDU(self._rows)
+
+    fits = types.ModuleType("astropy.io.fits")
+    fits.open = lambda filename: _HDUList(filename)
+    astropy = types.ModuleType("astropy")
+    astropy_io = types.ModuleType("astropy.io")
+    astropy.io = astropy_io
+    astropy_io.fits = fits
+    sys.modules.update({"astropy": astropy, "astropy.io": astropy_io, "astropy.io.fits": fits})
+
+    sys.modules["mbproj2"] = mbshim
+    sys.modules["mbproj2.physconstants"] = mbshim.physconstants
+
+    abel = types.ModuleType("abel")
+    direct = types.ModuleType("abel.direct")
+
+    def direct_transform(fr, dr=None, r=None, direction="inverse", derivative=None, int_func=None,
+                         correction=True, backend="C", **kw):
+        assert direction == "forward" and backend == "Python" and r is not None
+        return orc.pyabel_direct_forward(fr, r)
+
+    direct.direct_transform = direct_transform
+    abel.direct = direct
+    sys.modules.update({"abel": abel, "abel.direct": direct})
+    sys.modules["h5py"] = types.ModuleType("h5py")
+
+    import scipy.integrate
+    if not hasattr(scipy.integrate, "simps"):
+        scipy.integrate.simps = scipy.integrate.simpson
+    return mbshim
+
+
+def import_reference():
+    """Returns (ref_module, mb) with the reference's joxsz_funcs loaded from /root/reference."""
+    mb = _install_stubs()
+    spec = importlib.util.spec_from_file_location("ref_joxsz_funcs", os.path.join(REFERENCE_DIR, "joxsz_funcs.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    return ref, mb
