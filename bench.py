@@ -161,7 +161,7 @@ def run_reference_arm(args):
         return
     fit = build_cluster()
     pool, cores = make_pool()
-    per_step = max(cores * 8, 64)
+    per_step = max(cores * 16, 128)
     thetas = ensemble(fit, per_step * (args.steps + args.warmup))
     for w in range(args.warmup):
         cpu_reference_rate(thetas[w * per_step:(w + 1) * per_step], pool)
@@ -237,7 +237,7 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = W * args.steps / (ms * 1e-3)
-    acc = sampler.acceptance_fraction()
+    acc = sampler.mean_acceptance()
 
     # ---- end to end through the reference-facing vectorised call with host buffers (rank-local shard)
     shard = W // world
@@ -286,7 +286,7 @@ def run_gpu_arm(args):
         launches = int(sum(v[1] for v in stages.values())) + sampler.aux_launches
         # bounded CPU baseline on this box's cores
         pool, cores = make_pool()
-        sample_n = max(cores * 8, 64)
+        sample_n = max(cores * 32, 256)
         cpu_rate, cpu_dt, cpu_ll = cpu_reference_rate(host_theta[:sample_n], pool)
         pool.close()
         gpu_ll = eng(host_theta[:sample_n])

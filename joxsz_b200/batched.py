@@ -71,6 +71,8 @@ class BatchedLikelihood:
             return t
         a = np.ascontiguousarray(np.atleast_2d(np.asarray(theta, dtype=np.float64)))
         W = a.shape[0]
+        if a.ndim != 2 or a.shape[1] != self.ndim:
+            raise ValueError(f"theta must be [W, {self.ndim}], got {a.shape}")
         if self._pinned_in is None or self._pinned_in.shape[0] < W:
             self._pinned_in = torch.empty((max(W, 1), self.ndim), dtype=torch.float64).pin_memory()
         self._pinned_in[:W].copy_(torch.from_numpy(a))
@@ -92,6 +94,8 @@ class BatchedLikelihood:
         W = theta_dev.shape[0]
         if out is None:
             out = self._new(W)
+        if W == 0:              # an empty tensor has a NULL data pointer, which the C ABI rejects
+            return out
         with torch.cuda.device(self.device):
             rc = self.lib.jx_loglike(self._h, _ptr(theta_dev), W, _ptr(out), self._stream())
         _lib.check(rc, self._h)

@@ -126,7 +126,9 @@ def getLikelihood(self, vals=None):
         if single:
             self.updateThawed(theta)
     eng = engine_for(self, W)
-    ll = eng(theta if not single or isinstance(theta, torch.Tensor) else theta[None, :])
+    if not isinstance(theta, torch.Tensor):
+        theta = theta.reshape(-1, theta.shape[-1])       # [W, ndim]; W = 1 for a single vector
+    ll = eng(theta)
     if isinstance(ll, torch.Tensor) and ll.is_cuda:
         best_val, best_idx = (ll, 0) if ll.dim() == 0 else torch.max(ll, dim=0)
         best_val, best_idx = float(best_val), int(best_idx)
@@ -135,7 +137,7 @@ def getLikelihood(self, vals=None):
         best_idx = int(np.argmax(arr))
         best_val = float(arr[best_idx])
     if mb.fit.debugfit and (best_val - self.bestlike) > 0.1:
-        best_theta = theta if single else theta[best_idx]
+        best_theta = theta[best_idx] if theta.ndim == 2 else theta
         if isinstance(best_theta, torch.Tensor):
             best_theta = best_theta.detach().cpu().numpy()
         best_theta = np.asarray(best_theta, dtype=np.float64).reshape(-1)
@@ -143,6 +145,8 @@ def getLikelihood(self, vals=None):
         self.bestlike = best_val
         _write_fit_dat(self, eng, best_theta, best_val)
     if single:
+        if isinstance(ll, torch.Tensor):
+            return float(ll.reshape(-1)[0])
         return float(ll[0]) if np.ndim(ll) else float(ll)
     return ll
 

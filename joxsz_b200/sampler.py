@@ -1,0 +1,418 @@
+"""Device-resident ensemble sampler: emcee's stretch move driven by the batched likelihood.
+
+Replaces, for the path this repo accelerates, ``emcee.EnsembleSampler`` as the reference uses it
+(``joxsz_main.py:203-210``; iteration schedule ``joxsz_funcs.py:548-635``): instead of ``pool.map`` of
+one ``getLikelihood`` call per walker, each half-step proposes, evaluates and accepts every active
+walker at once on the GPU (``jx_stretch_propose`` -> ``jx_loglike`` -> ``jx_stretch_accept`` ->
+all-gather -> ``jx_stretch_scatter``).
+
+Multi-GPU: one process per GPU.  Every rank holds the whole ensemble (``coords [W, ndim]``, ``lp [W]``,
+kept identical by construction); in a half-step rank ``g`` handles the contiguous slice
+``[g*per, (g+1)*per)`` of the active colour and the only collective is one all-gather of the packed
+results ``[per, ndim + 2]`` (new position, new log-prob, accepted flag) per half-step.  Random numbers
+are counter based (Philox keyed by seed, walker, iteration), so the chain does not depend on the number
+of ranks.
+
+The sampler itself does no arithmetic: proposals, acceptance and scatter are CUDA kernels behind the
+C ABI (``ops=None``).  The ``ops`` hook exists so that the index/sharding logic can be exercised on CPU
+with a numpy model of those kernels (tests only); the product path raises without the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+
+
+class CudaStretchOps:
+    """``jx_stretch_*`` through ctypes (include/joxsz_b200.h)."""
+
+    launches_per_half_step = 3
+
+    def __init__(self, device: torch.device):
+        if device.type != "cuda":
+            raise _lib.JxError("the stretch-move kernels are CUDA only (no CPU implementation)")
+        self.lib = _lib.load()
+        self.device = device
+        self.index = device.index if device.index is not None else torch.cuda.current_device()
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def propose(self, coords, perm, split, r_first, r_count, a, seed, iteration, prop, factor):
+        nall, ndim = coords.shape
+        rc = self.lib.jx_stretch_propose(_ptr(coords), _ptr(perm), nall, ndim, split, r_first, r_count, float(a),
+                                         C.c_uint64(seed), C.c_uint64(iteration), _ptr(prop), _ptr(factor),
+                                         self.index, self._stream())
+        _lib.check(rc)
+
+    def accept(self, coords, lp, perm, split, r_first, r_count, prop, lp_new, factor, seed, iteration, packed):
+        nall, ndim = coords.shape
+        rc = self.lib.jx_stretch_accept(_ptr(coords), _ptr(lp), _ptr(perm), nall, ndim, split, r_first, r_count,
+                                        _ptr(prop), _ptr(lp_new), _ptr(factor), C.c_uint64(seed),
+                                        C.c_uint64(iteration), _ptr(packed), self.index, self._stream())
+        _lib.check(rc)
+
+    def scatter(self, coords, lp, naccept, perm, split, packed_all, ns):
+        nall, ndim = coords.shape
+        rc = self.lib.jx_stretch_scatter(_ptr(coords), _ptr(lp), _ptr(naccept), _ptr(perm), nall, ndim, split,
+                                         _ptr(packed_all), ns, self.index, self._stream())
+        _lib.check(rc)
+
+
+def shard_bounds(ns: int, world: int, rank: int):
+    """Slice of the ``ns`` active walkers of a half-step handled by ``rank``: (per, r_first, r_count).
+    ``per`` = ceil(ns / world) is the static row count every rank contributes to the all-gather."""
+    per = (ns + world - 1) // world
+    r_first = min(rank * per, ns)
+    r_count = max(0, min(per, ns - r_first))
+    return per, r_first, r_count
+
+
+def split_permutation(nall: int, seed: int, iteration: int) -> np.ndarray:
+    """Random permutation shared by all ranks; the colour of the walker at position p is p & 1, i.e.
+    emcee's ``inds = arange(n) % 2; random.shuffle(inds)`` (RedBlueMove.propose, randomize_split=True)."""
+    rng = np.random.Generator(np.random.Philox(key=int(seed) & (2**64 - 1), counter=[0, 0, 0, int(iteration)]))
+    return rng.permutation(nall).astype(np.int32)
+
+
+class State:
+    """What one iteration of :meth:`EnsembleSampler.sample` yields (emcee ``State`` look-alike);
+    arrays are copied to the host only when read."""
+
+    def __init__(self, sampler):
+        self._s = sampler
+        self.random_state = None
+        self.blobs = None
+
+    @property
+    def coords(self):
+        return self._s.coords_host()
+
+    @property
+    def log_prob(self):
+        return self._s.log_prob_host()
+
+    def __iter__(self):          # emcee-2 style unpacking: pos, lnprob, rstate = result[:3]
+        return iter((self.coords, self.log_prob, self.random_state))
+
+    def __getitem__(self, i):
+        return (self.coords, self.log_prob, self.random_state)[i]
+
+
+class EnsembleSampler:
+    """Subset of ``emcee.EnsembleSampler`` the reference touches, on device.
+
+    ``log_prob_fn``: a :class:`joxsz_b200.batched.BatchedLikelihood` (anything with
+    ``loglike_device(theta[W, ndim]) -> ll[W]``), or the bound ``fit.getLikelihood`` exactly as
+    ``joxsz_main.py:206`` passes it (its engine is looked up with :func:`joxsz_b200.funcs.engine_for`).
+    ``pool`` / ``backend`` are accepted and ignored (walkers are batched on the GPU; chains live in
+    memory, see :meth:`save_npz`).
+    """
+
+    def __init__(self, nwalkers, ndim, log_prob_fn, pool=None, backend=None, a=2.0, seed=None, world_size=1,
+                 rank=0, group=None, ops=None, device=None, vectorize=True, moves=None):
+        if nwalkers < 2 * ndim:
+            raise ValueError("The number of walkers needs to be at least twice the dimension of the problem")
+        if moves is not None:
+            raise ValueError("only the default StretchMove(a) is implemented")
+        self.nwalkers, self.ndim, self.a = int(nwalkers), int(ndim), float(a)
+        self.world, self.rank, self.group = int(world_size), int(rank), group
+        if seed is None:
+            seed = int(np.random.randint(0, 2**31 - 1))      # np.random.seed(seed) upstream (joxsz_main.py:204)
+        self.seed = int(seed)
+        self.per0 = shard_bounds((self.nwalkers + 1) // 2, self.world, self.rank)[0]
+        need = max(self.per0, shard_bounds(self.nwalkers, self.world, self.rank)[0])
+        self.fit = None
+        if hasattr(log_prob_fn, "loglike_device"):
+            self.engine = log_prob_fn
+        else:
+            fit = getattr(log_prob_fn, "__self__", None)
+            if fit is None or not hasattr(fit, "thawed"):
+                raise TypeError("log_prob_fn must be a BatchedLikelihood or the bound fit.getLikelihood")
+            from .funcs import engine_for
+            self.fit = fit
+            self.engine = engine_for(fit, need)
+        if self.engine.ndim != self.ndim:
+            raise ValueError(f"ndim={ndim} but the likelihood has {self.engine.ndim} thawed parameters")
+        if getattr(self.engine, "max_walkers", need) < need:
+            raise ValueError(f"likelihood engine capacity {self.engine.max_walkers} < {need} walkers per call")
+        self.device = torch.device(device) if device is not None else getattr(self.engine, "device", None)
+        if self.device is None:
+            raise ValueError("device unknown")
+        self.ops = ops if ops is not None else CudaStretchOps(self.device)
+        self.initspread = 0.1
+        self.pos0 = None
+        self.backend = self                   # mcmc.backend.get_chain()/get_log_prob()/reset(...)
+        self.iteration = 0                    # global Philox counter: never reset, so restarts do not repeat draws
+        self.aux_launches = 0
+        self._coords = self._lp = None
+        self._chain = self._chain_lp = None
+        self._nstored = 0
+        self._alloc()
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self):
+        dev, f64 = self.device, torch.float64
+        W, nd, per = self.nwalkers, self.ndim, self.per0
+        self._coords = torch.zeros((W, nd), dtype=f64, device=dev)
+        self._lp = torch.full((W,), -math.inf, dtype=f64, device=dev)
+        self._naccept = torch.zeros((W,), dtype=torch.int32, device=dev)
+        self._prop = torch.zeros((per, nd), dtype=f64, device=dev)
+        self._factor = torch.zeros((per,), dtype=f64, device=dev)
+        self._lpnew = torch.zeros((per,), dtype=f64, device=dev)
+        self._packed = torch.zeros((per, nd + 2), dtype=f64, device=dev)
+        self._packed_all = self._packed if self.world == 1 else torch.zeros((per * self.world, nd + 2), dtype=f64,
+                                                                            device=dev)
+        self._perm = torch.zeros((W,), dtype=torch.int32, device=dev)
+        self._perm_host = torch.zeros((W,), dtype=torch.int32)
+        if dev.type == "cuda":
+            self._perm_host = self._perm_host.pin_memory()
+        self._steps_done = 0
+
+    def _all_gather(self, out, inp):
+        import torch.distributed as dist
+        try:
+            dist.all_gather_into_tensor(out, inp, group=self.group)
+        except (RuntimeError, NotImplementedError):      # backends without the flat variant
+            parts = list(out.view(self.world, *inp.shape).unbind(0))
+            dist.all_gather(parts, inp, group=self.group)
+
+    # ------------------------------------------------------------------ state
+    def initialize(self, p0, log_prob=None):
+        """Load the starting ensemble [W, ndim]; log-probs are evaluated (sharded over ranks) if absent."""
+        p0 = np.ascontiguousarray(np.asarray(p0, dtype=np.float64))
+        if p0.shape != (self.nwalkers, self.ndim):
+            raise ValueError(f"incompatible input dimensions {p0.shape}")
+        if not np.all(np.isfinite(p0)):
+            raise ValueError("At least one parameter value was infinite or NaN")
+        self._coords.copy_(torch.from_numpy(p0))
+        if log_prob is not None:
+            self._lp.copy_(torch.from_numpy(np.asarray(log_prob, dtype=np.float64)))
+        else:
+            per, first, count = shard_bounds(self.nwalkers, self.world, self.rank)
+            mine = torch.full((per,), -math.inf, dtype=torch.float64, device=self.device)
+            if count:
+                mine[:count] = self.engine.loglike_device(self._coords[first:first + count].contiguous())
+            if self.world == 1:
+                self._lp.copy_(mine[:self.nwalkers])
+            else:
+                full = torch.empty((per * self.world,), dtype=torch.float64, device=self.device)
+                self._all_gather(full, mine)
+                self._lp.copy_(full[:self.nwalkers])
+        if bool(torch.isnan(self._lp).any()):
+            raise ValueError("Probability function returned NaN")
+        self._naccept.zero_()
+        self._steps_done = 0
+
+    def coords_host(self):
+        return self._coords.cpu().numpy()
+
+    def log_prob_host(self):
+        return self._lp.cpu().numpy()
+
+    def evals_per_rank_per_launch(self):
+        return self.per0
+
+    # ------------------------------------------------------------------ one ensemble iteration
+    def step(self):
+        """One stretch-move iteration: two half-steps, every walker proposed and evaluated once."""
+        W = self.nwalkers
+        it = self.iteration
+        self._perm_host.copy_(torch.from_numpy(split_permutation(W, self.seed, it)))
+        self._perm.copy_(self._perm_host, non_blocking=True)
+        for split in (0, 1):
+            ns = (W - split + 1) // 2
+            per, first, count = shard_bounds(ns, self.world, self.rank)
+            if count:
+                prop = self._prop[:count]
+                self.ops.propose(self._coords, self._perm, split, first, count, self.a, self.seed, it, prop,
+                                 self._factor)
+                self.engine.loglike_device(prop, out=self._lpnew[:count])
+                self.ops.accept(self._coords, self._lp, self._perm, split, first, count, prop, self._lpnew,
+                                self._factor, self.seed, it, self._packed)
+            if self.world > 1:
+                # static shape [per0, ndim+2] per rank; rows beyond `ns` are never read by scatter
+                self._all_gather(self._packed_all, self._packed)
+                if per != self.per0:       # odd ensembles: the second colour has one walker fewer -> re-pack rows
+                    pa = self._packed_all.view(self.world, self.per0, -1)[:, :per].reshape(-1, self.ndim + 2)
+                    pa = pa.contiguous()
+                else:
+                    pa = self._packed_all
+            else:
+                pa = self._packed
+            self.ops.scatter(self._coords, self._lp, self._naccept, self._perm, split, pa, ns)
+            self.aux_launches += self.ops.launches_per_half_step
+        self.iteration += 1
+        self._steps_done += 1
+
+    # ------------------------------------------------------------------ emcee-like driver API
+    def reset(self, nwalkers=None, ndim=None):
+        """``backend.reset(nwalkers, ndim)`` / ``sampler.reset()``: drop the stored chain."""
+        if nwalkers is not None and (int(nwalkers), int(ndim)) != (self.nwalkers, self.ndim):
+            raise ValueError("cannot change the ensemble shape of a device sampler")
+        self._chain = self._chain_lp = None
+        self._nstored = 0
+        self._naccept.zero_()
+        self._steps_done = 0
+
+    def sample(self, initial_state, iterations=1, thin_by=1, thin=None, store=True, storechain=None, progress=False,
+               log_prob0=None):
+        """Generator over iterations, emcee 3 conventions: ``thin_by=k`` runs ``iterations*k`` steps and
+        stores/yields every k-th; the deprecated ``thin=k`` runs ``iterations`` steps, stores every k-th,
+        yields every step (this is the form the reference uses, ``joxsz_funcs.py:593-622``)."""
+        if storechain is not None:
+            store = storechain
+        if isinstance(initial_state, State):
+            initial_state = initial_state.coords
+        self.initialize(np.asarray(initial_state), log_prob0)
+        if thin is not None:
+            thin = int(thin)
+            if thin <= 0:
+                raise ValueError("Invalid thinning argument")
+            yield_step, checkpoint_step, total = 1, thin, int(iterations)
+            nsave = int(iterations) // thin
+        else:
+            thin_by = int(thin_by)
+            if thin_by <= 0:
+                raise ValueError("Invalid thinning argument")
+            yield_step = checkpoint_step = thin_by
+            total = int(iterations) * thin_by
+            nsave = int(iterations)
+        if store:
+            self._grow(nsave)
+        bar = None
+        if progress:
+            try:
+                from tqdm import tqdm
+                bar = tqdm(total=total)
+            except Exception:
+                bar = None
+        state = State(self)
+        for i in range(1, total + 1):
+            self.step()
+            if store and i % checkpoint_step == 0:
+                self._chain[self._nstored].copy_(self._coords)
+                self._chain_lp[self._nstored].copy_(self._lp)
+                self._nstored += 1
+            if bar is not None:
+                bar.update(1)
+            if i % yield_step == 0:
+                yield state
+        if bar is not None:
+            bar.close()
+
+    def run_mcmc(self, initial_state, nsteps, **kw):
+        state = None
+        for state in self.sample(initial_state, iterations=nsteps, **kw):
+            pass
+        return state
+
+    def _grow(self, nsave):
+        need = self._nstored + nsave
+        if self._chain is None:
+            self._chain = torch.empty((need, self.nwalkers, self.ndim), dtype=torch.float64, device=self.device)
+            self._chain_lp = torch.empty((need, self.nwalkers), dtype=torch.float64, device=self.device)
+        elif self._chain.shape[0] < need:
+            c = torch.empty((need, self.nwalkers, self.ndim), dtype=torch.float64, device=self.device)
+            l = torch.empty((need, self.nwalkers), dtype=torch.float64, device=self.device)
+            c[:self._nstored] = self._chain[:self._nstored]
+            l[:self._nstored] = self._chain_lp[:self._nstored]
+            self._chain, self._chain_lp = c, l
+
+    def get_chain(self, flat=False, thin=1, discard=0):
+        if self._chain is None or self._nstored == 0:
+            raise AttributeError("you must run the sampler with 'store == True' before accessing the results")
+        v = self._chain[discard:self._nstored:thin].cpu().numpy()
+        return v.reshape(-1, self.ndim) if flat else v
+
+    def get_log_prob(self, flat=False, thin=1, discard=0):
+        if self._chain_lp is None or self._nstored == 0:
+            raise AttributeError("you must run the sampler with 'store == True' before accessing the results")
+        v = self._chain_lp[discard:self._nstored:thin].cpu().numpy()
+        return v.reshape(-1) if flat else v
+
+    @property
+    def chain(self):
+        """[nwalkers, nsteps, ndim] (emcee's legacy layout, read at ``joxsz_main.py:213``)."""
+        return np.swapaxes(self.get_chain(), 0, 1)
+
+    @property
+    def acceptance_fraction(self):
+        return self._naccept.cpu().numpy() / max(self._steps_done, 1)
+
+    def mean_acceptance(self):
+        return float(self._naccept.double().mean().item()) / max(self._steps_done, 1)
+
+    def save_npz(self, path, **attrs):
+        """Chain in emcee's HDF layout names (``chain`` [nsteps, W, ndim], ``log_prob`` [nsteps, W],
+        ``accepted`` [W]) as a compressed ``.npz`` (h5py is not required)."""
+        np.savez_compressed(path, chain=self.get_chain(), log_prob=self.get_log_prob(),
+                            accepted=self._naccept.cpu().numpy(), iteration=np.array(self._steps_done),
+                            **{k: np.asarray(v) for k, v in attrs.items()})
+
+
+# ----------------------------------------------------------------------------------------------
+# iteration schedule of the reference (joxsz_funcs.py:548-635)
+# ----------------------------------------------------------------------------------------------
+
+def _generateInitPars(mcmc, fit, rng=None):
+    """Initial ball ``p = theta_hat * (1 + N(0, initspread))`` keeping only finite-likelihood draws
+    (reference ``joxsz_funcs.py:548-570``); candidates are evaluated a batch at a time."""
+    thawedpars = np.array(fit.thawedParVals(), dtype=np.float64)
+    assert np.all(np.isfinite(thawedpars))
+    walks, dim = mcmc.nwalkers, mcmc.ndim
+    rng = np.random if rng is None else rng
+    cap = int(getattr(mcmc.engine, "max_walkers", walks))
+    p0 = np.empty((0, dim))
+    tries = 0
+    while p0.shape[0] < walks:
+        n = min(cap, max(2 * (walks - p0.shape[0]), 16))
+        cand = thawedpars * (1 + rng.normal(0., mcmc.initspread, size=(n, dim)))
+        ll = mcmc.engine(cand)
+        p0 = np.concatenate([p0, cand[np.isfinite(ll)]], axis=0)
+        tries += 1
+        if tries > 1000:
+            raise RuntimeError("could not draw an initial ensemble with finite likelihood")
+    return p0[:walks]
+
+
+def mcmc_run(mcmc, fit, nburn, nsteps, nthin=1, autorefit=True, minfrac=0.2, minimprove=0.01, max_prefit=None):
+    """MCMC execution with the reference's schedule (``joxsz_funcs.py:572-635``): preliminary 1000-iteration
+    rounds repeated while the best log-probability improves, burn-in, then the stored chain.
+    ``max_prefit`` optionally bounds the number of preliminary rounds (the reference's loop is unbounded)."""
+    eng = mcmc.engine
+    bestprob = float(eng(np.asarray(fit.thawedParVals(), dtype=np.float64)))
+    newlike = bestprob
+    p0 = _generateInitPars(mcmc, fit)
+    print('Preliminary fit (1000 iterations) to improve likelihood')
+    rounds = 0
+    while newlike >= bestprob:
+        bestprob = newlike
+        for _ in mcmc.sample(p0, thin=500, iterations=1000, progress=False):
+            pass
+        newlike = float(mcmc.backend.get_log_prob()[-1, :].max())
+        p0 = mcmc.backend.get_chain()[-1, :, :]
+        mcmc.backend.reset(mcmc.nwalkers, len(fit.thawedParVals()))
+        rounds += 1
+        if max_prefit is not None and rounds >= max_prefit:
+            break
+    print('Burn-in period')
+    for _ in mcmc.sample(p0, thin=max(nburn // 2, 1), iterations=nburn, progress=False):
+        pass
+    p1 = mcmc.backend.get_chain()[-1, :, :]
+    mcmc.backend.reset(mcmc.nwalkers, len(fit.thawedParVals()))
+    print('Starting sampling')
+    for _ in mcmc.sample(p1, thin=nthin, iterations=nsteps, progress=False):
+        pass
+    print('Finished sampling')
+    print('Acceptance fraction: %s' % np.mean(mcmc.acceptance_fraction))
+    return True

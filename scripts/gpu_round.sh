@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/ncu_launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k3_szmap -s 2 -c 1 -f -o gpurun_out/k3_full python bench.py --steps 2 --warmup 1 > gpurun_out/ncu_k3.log 2>&1
+nvidia-smi > gpurun_out/nvidia_smi.txt; lscpu | head -20 > gpurun_out/lscpu.txt

@@ -53,3 +53,122 @@ def model_tail(pk, row, tsz, calib):
     model = bright @ pk.g_op.T
     z = ((pk.flux - model) / pk.flux_err) ** 2
     return dict(bright=bright, model=model, chisq=np.nansum(z, axis=1))
+
+
+# ---------------------------------------------------------------------------------------------
+# K6: numpy model of the stretch-move kernels (Philox4x32-10 counter RNG) -- lets the sampler's
+# sharding / index logic run on CPU (gloo, world_size 2) and pins the CUDA kernels' random streams.
+# ---------------------------------------------------------------------------------------------
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10; all arguments uint32 arrays (broadcastable). Returns 4 uint32 arrays."""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    W0, W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+    c0, c1, c2, c3, k0, k1 = (np.asarray(v, dtype=np.uint32) for v in (c0, c1, c2, c3, k0, k1))
+    c0, c1, c2, c3, k0, k1 = np.broadcast_arrays(c0, c1, c2, c3, k0, k1)
+    c0, c1, c2, c3, k0, k1 = (v.copy() for v in (c0, c1, c2, c3, k0, k1))
+    with np.errstate(over="ignore"):
+        for _ in range(10):
+            p0 = M0 * c0.astype(np.uint64)
+            p1 = M1 * c2.astype(np.uint64)
+            n0 = (p1 >> np.uint64(32)).astype(np.uint32) ^ c1 ^ k0
+            n1 = p1.astype(np.uint32)
+            n2 = (p0 >> np.uint64(32)).astype(np.uint32) ^ c3 ^ k1
+            n3 = p0.astype(np.uint32)
+            c0, c1, c2, c3 = n0, n1, n2, n3
+            k0 = k0 + W0
+            k1 = k1 + W1
+    return c0, c1, c2, c3
+
+
+def _u01(hi, lo):
+    x = (hi.astype(np.uint64) << np.uint64(32)) | lo.astype(np.uint64)
+    return (x >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def _draws(k, seed, iteration, split, purpose):
+    seed, iteration = int(seed), int(iteration)
+    return philox4x32_10(k.astype(np.uint32), np.uint32(iteration & 0xFFFFFFFF), np.uint32(iteration >> 32),
+                         np.uint32((split << 1) | purpose), np.uint32(seed & 0xFFFFFFFF), np.uint32(seed >> 32))
+
+
+def stretch_propose(coords, perm, split, r_first, r_count, a, seed, iteration):
+    nall, ndim = coords.shape
+    i = np.arange(r_count)
+    k = perm[2 * (r_first + i) + split]
+    r0, r1, r2, _ = _draws(k, seed, iteration, split, 0)
+    u = _u01(r0, r1)
+    root = (a - 1.0) * u + 1.0
+    z = root * root / a
+    other = 1 - split
+    nc = (nall - other + 1) // 2
+    rint = ((r2.astype(np.uint64) * np.uint64(nc)) >> np.uint64(32)).astype(np.int64)
+    s = coords[k]
+    c = coords[perm[2 * rint + other]]
+    prop = c - (c - s) * z[:, None]
+    factor = (ndim - 1.0) * np.log(z)
+    return prop, factor
+
+
+def stretch_accept(coords, lp, perm, split, r_first, r_count, prop, lp_new, factor, seed, iteration):
+    ndim = coords.shape[1]
+    i = np.arange(r_count)
+    k = perm[2 * (r_first + i) + split]
+    r0, r1, _, _ = _draws(k, seed, iteration, split, 1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lnu = np.log(_u01(r0, r1))
+        acc = (factor + lp_new - lp[k]) > lnu
+    packed = np.empty((r_count, ndim + 2))
+    packed[:, :ndim] = np.where(acc[:, None], prop, coords[k])
+    packed[:, ndim] = np.where(acc, lp_new, lp[k])
+    packed[:, ndim + 1] = acc.astype(np.float64)
+    return packed
+
+
+def stretch_scatter(coords, lp, naccept, perm, split, packed_all, ns):
+    ndim = coords.shape[1]
+    k = perm[2 * np.arange(ns) + split]
+    coords[k] = packed_all[:ns, :ndim]
+    lp[k] = packed_all[:ns, ndim]
+    naccept[k] += (packed_all[:ns, ndim + 1] != 0).astype(naccept.dtype)
+
+
+class NumpyStretchOps:
+    """Same interface as joxsz_b200.sampler.CudaStretchOps, on CPU torch tensors (tests only)."""
+    launches_per_half_step = 3
+
+    def propose(self, coords, perm, split, r_first, r_count, a, seed, iteration, prop, factor):
+        p, f = stretch_propose(coords.numpy(), perm.numpy(), split, r_first, r_count, a, seed, iteration)
+        prop.numpy()[:r_count] = p
+        factor.numpy()[:r_count] = f
+
+    def accept(self, coords, lp, perm, split, r_first, r_count, prop, lp_new, factor, seed, iteration, packed):
+        packed.numpy()[:r_count] = stretch_accept(coords.numpy(), lp.numpy(), perm.numpy(), split, r_first, r_count,
+                                                  prop.numpy()[:r_count], lp_new.numpy()[:r_count],
+                                                  factor.numpy()[:r_count], seed, iteration)
+
+    def scatter(self, coords, lp, naccept, perm, split, packed_all, ns):
+        stretch_scatter(coords.numpy(), lp.numpy(), naccept.numpy(), perm.numpy(), split, packed_all.numpy(), ns)
+
+
+class GaussianToyLikelihood:
+    """log N(0, diag(sig^2)) on CPU torch tensors with the engine interface the sampler needs."""
+
+    def __init__(self, ndim, max_walkers=1 << 20):
+        import torch
+        self.ndim, self.max_walkers = ndim, max_walkers
+        self.device = torch.device("cpu")
+        self.sig = torch.linspace(0.5, 2.0, ndim, dtype=torch.float64)
+        self.calls = []
+
+    def loglike_device(self, theta, out=None):
+        ll = -0.5 * ((theta / self.sig) ** 2).sum(dim=1)
+        self.calls.append(theta.shape[0])
+        if out is not None:
+            out.copy_(ll)
+            return out
+        return ll
+
+    def __call__(self, theta):
+        import torch
+        return self.loglike_device(torch.from_numpy(np.atleast_2d(np.asarray(theta, float)))).numpy()

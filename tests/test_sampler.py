@@ -1,0 +1,216 @@
+"""Ensemble sampler: sharding / index logic on CPU (numpy model of the K6 kernels, gloo world_size 2),
+the CUDA K6 kernels against that model, and the device sampler's emcee semantics on the GPU."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import kernel_model as km
+from joxsz_b200.sampler import EnsembleSampler, shard_bounds, split_permutation
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+# ------------------------------------------------------------------------------------------- host logic
+
+def test_shard_bounds_cover_exactly():
+    for ns in (0, 1, 7, 15, 16, 32768, 32769):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            per0 = shard_bounds(ns, world, 0)[0]
+            for r in range(world):
+                per, first, count = shard_bounds(ns, world, r)
+                assert per == per0 and count <= per
+                assert first == min(r * per, ns)
+                seen += list(range(first, first + count))
+            assert seen == list(range(ns))
+
+
+def test_split_permutation_is_shared_and_balanced():
+    p = split_permutation(101, 7, 3)
+    assert np.array_equal(p, split_permutation(101, 7, 3))
+    assert sorted(p.tolist()) == list(range(101))
+    assert not np.array_equal(p, split_permutation(101, 7, 4))
+    assert not np.array_equal(p, split_permutation(101, 8, 3))
+    # colour of position q is q & 1: 51 walkers in colour 0, 50 in colour 1, like emcee's arange(n) % 2 shuffled
+    assert len(p[0::2]) == 51 and len(p[1::2]) == 50
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10."""
+    z = np.uint32(0)
+    out = km.philox4x32_10(z, z, z, z, z, z)
+    assert [int(v) for v in out] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = np.uint32(0xffffffff)
+    out = km.philox4x32_10(f, f, f, f, f, f)
+    assert [int(v) for v in out] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    out = km.philox4x32_10(np.uint32(0x243f6a88), np.uint32(0x85a308d3), np.uint32(0x13198a2e), np.uint32(0x03707344),
+                           np.uint32(0xa4093822), np.uint32(0x299f31d0))
+    assert [int(v) for v in out] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def _run_cpu_sampler(W, ndim, steps, world=1, rank=0, group=None, seed=11):
+    eng = km.GaussianToyLikelihood(ndim)
+    s = EnsembleSampler(W, ndim, eng, seed=seed, world_size=world, rank=rank, group=group,
+                        ops=km.NumpyStretchOps(), device="cpu")
+    p0 = np.random.default_rng(5).normal(size=(W, ndim))
+    s.initialize(p0)
+    for _ in range(steps):
+        s.step()
+    return s, eng
+
+
+def test_cpu_model_sampler_statistics():
+    """Stretch move on a Gaussian target: acceptance in the usual range, variances recovered."""
+    W, ndim = 256, 4
+    eng = km.GaussianToyLikelihood(ndim)
+    s = EnsembleSampler(W, ndim, eng, seed=3, ops=km.NumpyStretchOps(), device="cpu")
+    p0 = np.random.default_rng(1).normal(size=(W, ndim))
+    for _ in s.sample(p0, iterations=300, thin_by=1):
+        pass
+    acc = s.acceptance_fraction.mean()
+    assert 0.3 < acc < 0.9
+    chain = s.get_chain(discard=100, flat=True)
+    assert np.allclose(chain.std(axis=0), eng.sig.numpy(), rtol=0.1)
+    assert s.chain.shape == (W, 300, ndim)
+    assert set(eng.calls[1:]) == {W // 2}          # every half-step evaluates half the ensemble in one call
+    lp = s.get_log_prob()
+    assert np.allclose(lp[-1], -0.5 * ((s.get_chain()[-1] / eng.sig.numpy()) ** 2).sum(axis=1))
+
+
+def test_emcee_thin_conventions():
+    W, ndim = 16, 3
+    s = EnsembleSampler(W, ndim, km.GaussianToyLikelihood(ndim), seed=3, ops=km.NumpyStretchOps(), device="cpu")
+    p0 = np.random.default_rng(1).normal(size=(W, ndim))
+    n = sum(1 for _ in s.sample(p0, thin=5, iterations=20))
+    assert n == 20 and s.get_chain().shape == (4, W, ndim)
+    s.reset(W, ndim)
+    n = sum(1 for _ in s.sample(p0, thin_by=5, iterations=4))
+    assert n == 4 and s.get_chain().shape == (4, W, ndim)
+    with pytest.raises(ValueError):
+        EnsembleSampler(5, 3, km.GaussianToyLikelihood(3), ops=km.NumpyStretchOps(), device="cpu")
+    with pytest.raises(ValueError):
+        s.initialize(np.full((W, ndim), np.nan))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, W, ndim, steps, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    s, eng = _run_cpu_sampler(W, ndim, steps, world=world, rank=rank, group=dist.group.WORLD)
+    q.put((rank, s.coords_host(), s.log_prob_host(), s.acceptance_fraction, eng.calls))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("W", [64, 37])
+def test_two_ranks_reproduce_single_rank_chain(W):
+    """world_size 2 over gloo: both ranks end with the same ensemble, bit-identical to the 1-rank run
+    (counter-based RNG), each evaluating only its slice."""
+    import torch.multiprocessing as mp
+    ndim, steps, world = 5, 6, 2
+    ref, _ = _run_cpu_sampler(W, ndim, steps)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, W, ndim, steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, coords, lp, acc, calls in res:
+        assert np.array_equal(coords, ref.coords_host())
+        assert np.array_equal(lp, ref.log_prob_host())
+        assert np.array_equal(acc, ref.acceptance_fraction)
+        assert max(calls) <= (W + 1) // 2 // world + 1 + (W // world)       # never the whole half-ensemble
+    assert res[0][4][1] + res[1][4][1] == (W + 1) // 2                      # first half-step: slices add up
+
+
+# ------------------------------------------------------------------------------------------- GPU
+
+@pytest.mark.gpu
+def test_k6_kernels_match_numpy_model():
+    from joxsz_b200.sampler import CudaStretchOps
+    dev = torch.device("cuda", 0)
+    ops = CudaStretchOps(dev)
+    rng = np.random.default_rng(0)
+    for nall, ndim in ((64, 13), (101, 7)):
+        coords = rng.normal(size=(nall, ndim))
+        lp = rng.normal(size=nall)
+        perm = split_permutation(nall, 5, 9)
+        seed, it = 0x1234567890ABCDEF, (1 << 33) + 17
+        for split in (0, 1):
+            ns = (nall - split + 1) // 2
+            first, count = 3, ns - 5
+            prop_m, fac_m = km.stretch_propose(coords, perm, split, first, count, 2.0, seed, it)
+            c_d, p_d = torch.from_numpy(coords).to(dev), torch.from_numpy(perm).to(dev)
+            prop = torch.zeros((count, ndim), dtype=torch.float64, device=dev)
+            fac = torch.zeros(count, dtype=torch.float64, device=dev)
+            ops.propose(c_d, p_d, split, first, count, 2.0, seed, it, prop, fac)
+            assert np.allclose(prop.cpu().numpy(), prop_m, rtol=0, atol=1e-14)
+            assert np.allclose(fac.cpu().numpy(), fac_m, rtol=1e-14, atol=1e-15)
+            lp_new = rng.normal(size=count)
+            lp_new[::7] = -np.inf
+            pk_m = km.stretch_accept(coords, lp, perm, split, first, count, prop.cpu().numpy(), lp_new,
+                                     fac.cpu().numpy(), seed, it)
+            packed = torch.zeros((count, ndim + 2), dtype=torch.float64, device=dev)
+            ops.accept(c_d, torch.from_numpy(lp).to(dev), p_d, split, first, count, prop,
+                       torch.from_numpy(lp_new).to(dev), fac, seed, it, packed)
+            assert np.array_equal(packed.cpu().numpy(), pk_m)
+            assert 0 < pk_m[:, -1].sum() < count
+            # scatter of a full half
+            full = rng.normal(size=(ns, ndim + 2))
+            full[:, -1] = rng.integers(0, 2, ns)
+            c2, l2, n2 = coords.copy(), lp.copy(), np.zeros(nall, dtype=np.int32)
+            km.stretch_scatter(c2, l2, n2, perm, split, full, ns)
+            cd, ld = torch.from_numpy(coords).to(dev), torch.from_numpy(lp).to(dev)
+            nd = torch.zeros(nall, dtype=torch.int32, device=dev)
+            ops.scatter(cd, ld, nd, p_d, split, torch.from_numpy(full).to(dev), ns)
+            assert np.array_equal(cd.cpu().numpy(), c2) and np.array_equal(ld.cpu().numpy(), l2)
+            assert np.array_equal(nd.cpu().numpy(), n2)
+
+
+@pytest.mark.gpu
+def test_device_sampler_on_the_cluster_likelihood(cl1226_fit, cl1226_oracle):
+    """The device sampler on the real likelihood: log-probs carried by the chain equal the oracle's
+    likelihood of the carried positions; detailed-balance bookkeeping (rejected walkers do not move)."""
+    from helpers import orc
+    from joxsz_b200.batched import BatchedLikelihood
+    from joxsz_b200.synthetic import draw_parameters
+    eng = BatchedLikelihood(cl1226_fit, max_walkers=256)
+    W = 64
+    p0 = draw_parameters(cl1226_fit.thawed, n=W, seed=8, spread=0.01)
+    s = EnsembleSampler(W, eng.ndim, eng, seed=21)
+    s.initialize(p0)
+    assert np.isfinite(s.log_prob_host()).all()
+    before = s.coords_host().copy()
+    s.step()
+    after, lp = s.coords_host(), s.log_prob_host()
+    acc = s.acceptance_fraction
+    moved = np.any(after != before, axis=1)
+    assert np.array_equal(moved, acc > 0)
+    for _ in range(4):
+        s.step()
+    coords, lp = s.coords_host(), s.log_prob_host()
+    ref = orc.BatchedOracle(cl1226_oracle).loglike(coords)
+    assert np.max(np.abs(ref - lp)) < 1e-6
+    assert 0.05 < acc.mean() <= 1.0
+    # bound-method form, as joxsz_main.py:206 constructs the sampler
+    s2 = EnsembleSampler(W, len(cl1226_fit.thawed), cl1226_fit.getLikelihood, pool=None, seed=21)
+    s2.initialize(p0)
+    for _ in range(5):
+        s2.step()
+    assert np.array_equal(s2.coords_host(), coords)
+    eng.close()
