@@ -23,7 +23,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -80,28 +79,33 @@ class ClockSampler:
     def __init__(self, index=0):
         self.index = index
         self.samples = []
-        self._stop = threading.Event()
-        self._th = None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                if out.returncode == 0 and out.stdout.strip():
-                    self.samples.append([x.strip() for x in out.stdout.strip().split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self._proc = None
 
     def __enter__(self):
-        self._th = threading.Thread(target=self._run, daemon=True)
-        self._th.start()
+        # one long-lived nvidia-smi sampling every 50 ms (spawning it per sample is too slow for short runs)
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                           "--format=csv,noheader,nounits", "-lms", "50"],
+                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)           # first sample lands before the timed region starts
+        except Exception:
+            self._proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._th.join(timeout=6)
+        if self._proc is None:
+            return
+        time.sleep(0.06)
+        self._proc.terminate()
+        try:
+            out, _ = self._proc.communicate(timeout=5)
+        except Exception:
+            self._proc.kill()
+            out = ""
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) >= 7:
+                self.samples.append(f)
 
     def summary(self):
         if not self.samples:
@@ -316,7 +320,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--walkers", type=int, default=TOTAL_WALKERS)

@@ -20,6 +20,7 @@
 #ifndef JOXSZ_B200_H
 #define JOXSZ_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -182,7 +183,7 @@ int jx_radial_profiles(const double* pars, int32_t W, int32_t dens_mode, const d
 /* ---- ensemble stretch move (emcee RedBlueMove/StretchMove semantics; joxsz_main.py:206-210).
  * Every rank holds the whole ensemble `coords` [nall, ndim], `lp` [nall] (kept identical by the
  * all-gather of each half-step's results).  `perm` [nall] is a random permutation of 0..nall-1 shared
- * by all ranks; the colour of the walker at position p of `perm` is p & 1 (emcee:
+ * by all ranks (jx_stretch_permutation); the colour of the walker at position p of `perm` is p & 1 (emcee:
  * `inds = arange(n) % 2; shuffle(inds)`).  In the half-step `split` the active walkers are
  * perm[2 r + split], r = 0..ns-1 with ns = (nall - split + 1) / 2; a rank processes the contiguous slice
  * r in [r_first, r_first + r_count) -- equal, fixed-size work per rank whatever the colouring.
@@ -200,6 +201,11 @@ int jx_stretch_accept(const double* coords, const double* lp, const int32_t* per
                       int32_t split, int32_t r_first, int32_t r_count, const double* prop, const double* lp_new,
                       const double* factor, uint64_t seed, uint64_t iteration,
                       double* packed /*[r_count, ndim+2]*/, int32_t device, void* stream);
+/* permutation: perm = argsort of 64 Philox bits per walker (stable), a uniformly random permutation that
+ * depends only on (seed, iteration) -- identical on every rank, generated on the device.
+ * Call with workspace == NULL to get the required size in *workspace_bytes. */
+int jx_stretch_permutation(int32_t* perm, int32_t nall, uint64_t seed, uint64_t iteration, void* workspace,
+                           size_t* workspace_bytes, int32_t device, void* stream);
 /* scatter: write the gathered results of all ranks, packed_all [>= ns, ndim+2] in r order, back into
  * coords / lp and add the acceptance flags to naccept [nall]. */
 int jx_stretch_scatter(double* coords, double* lp, int32_t* naccept, const int32_t* perm, int32_t nall,

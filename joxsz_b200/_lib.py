@@ -66,6 +66,8 @@ PROTOTYPES = {
                                      C.c_uint64, C.c_uint64, _vp, _vp, C.c_int32, _vp]),
     "jx_stretch_accept": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     _vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, C.c_int32, _vp]),
+    "jx_stretch_permutation": (C.c_int, [_vp, C.c_int32, C.c_uint64, C.c_uint64, _vp, C.POINTER(C.c_size_t),
+                                         C.c_int32, _vp]),
     "jx_stretch_scatter": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int32,
                                      C.c_int32, _vp]),
     "jx_set_profiling": (C.c_int, [_vp, C.c_int32]),

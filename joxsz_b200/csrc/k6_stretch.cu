@@ -6,6 +6,8 @@
 // by jx_loglike.  Random numbers come from Philox4x32-10 keyed by the run seed with the counter
 // (global walker index, iteration, split | purpose), so a chain is bit-identical however the
 // ensemble is sharded over GPUs.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "jx_common.cuh"
 
 namespace {
@@ -33,7 +35,7 @@ JX_HD double u01(uint32_t hi, uint32_t lo) {       // 53-bit uniform in [0, 1)
     return (double)(x >> 11) * (1.0 / 9007199254740992.0);
 }
 
-constexpr uint32_t PURPOSE_PROPOSE = 0u, PURPOSE_ACCEPT = 1u;
+constexpr uint32_t PURPOSE_PROPOSE = 0u, PURPOSE_ACCEPT = 1u, PURPOSE_SHUFFLE = 2u;
 
 __global__ void k6_propose_kernel(const double* __restrict__ coords, const int32_t* __restrict__ perm, int nall,
                                   int ndim, int split, int r_first, int r_count, double a, uint64_t seed,
@@ -88,7 +90,46 @@ __global__ void k6_scatter_kernel(double* __restrict__ coords, double* __restric
     if (naccept && o[ndim + 1] != 0.0) naccept[k] += 1;
 }
 
+// sort keys of the colouring permutation: 64 random bits per walker (ties are broken by the stable sort)
+__global__ void k6_shuffle_keys_kernel(uint64_t* __restrict__ keys, int32_t* __restrict__ vals, int nall, uint64_t seed,
+                                       uint64_t iteration) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nall) return;
+    philox4 r = philox4x32_10((uint32_t)i, (uint32_t)iteration, (uint32_t)(iteration >> 32), PURPOSE_SHUFFLE,
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    keys[i] = ((uint64_t)r.v[0] << 32) | r.v[1];
+    vals[i] = i;
+}
+
 }  // namespace
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+extern "C" int jx_stretch_permutation(int32_t* perm, int32_t nall, uint64_t seed, uint64_t iteration, void* workspace,
+                                      size_t* workspace_bytes, int32_t device, void* stream) {
+    if (nall < 1 || !workspace_bytes) return JX_ERR_INVALID;
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                    (const int32_t*)nullptr, (int32_t*)nullptr, nall);
+    const size_t kb = align256(sizeof(uint64_t) * (size_t)nall), vb = align256(sizeof(int32_t) * (size_t)nall);
+    const size_t need = 2 * kb + vb + align256(cub_bytes);
+    if (!workspace) {                 // size query
+        *workspace_bytes = need;
+        return JX_OK;
+    }
+    if (!perm || *workspace_bytes < need) return JX_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)workspace;
+    uint64_t* keys_in = (uint64_t*)base;
+    uint64_t* keys_out = (uint64_t*)(base + kb);
+    int32_t* vals_in = (int32_t*)(base + 2 * kb);
+    void* tmp = base + 2 * kb + vb;
+    k6_shuffle_keys_kernel<<<(nall + 255) / 256, 256, 0, st>>>(keys_in, vals_in, nall, seed, iteration);
+    if (cub::DeviceRadixSort::SortPairs(tmp, cub_bytes, keys_in, keys_out, vals_in, perm, nall, 0, 64, st) != cudaSuccess)
+        return JX_ERR_CUDA;
+    return cudaGetLastError() == cudaSuccess ? JX_OK : JX_ERR_CUDA;
+}
 
 static bool slice_ok(int nall, int split, int r_first, int r_count) {
     if (nall < 2 || (split != 0 && split != 1) || r_first < 0 || r_count < 0) return false;

@@ -36,6 +36,7 @@ class CudaStretchOps:
     """``jx_stretch_*`` through ctypes (include/joxsz_b200.h)."""
 
     launches_per_half_step = 3
+    launches_per_permutation = 5        # key kernel + CUB radix sort passes (64-bit keys, onesweep)
 
     def __init__(self, device: torch.device):
         if device.type != "cuda":
@@ -43,9 +44,25 @@ class CudaStretchOps:
         self.lib = _lib.load()
         self.device = device
         self.index = device.index if device.index is not None else torch.cuda.current_device()
+        self._ws = None
+        self._ws_n = self._ws_bytes = 0
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def permutation(self, perm, seed, iteration):
+        """Colouring permutation of this iteration, generated on the device (identical on every rank)."""
+        nall = perm.shape[0]
+        if self._ws is None or self._ws_n != nall:
+            need = C.c_size_t(0)
+            _lib.check(self.lib.jx_stretch_permutation(None, nall, C.c_uint64(0), C.c_uint64(0), None,
+                                                       C.byref(need), self.index, None))
+            self._ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+            self._ws_n, self._ws_bytes = nall, need.value
+        nbytes = C.c_size_t(self._ws_bytes)
+        rc = self.lib.jx_stretch_permutation(_ptr(perm), nall, C.c_uint64(seed), C.c_uint64(iteration),
+                                             _ptr(self._ws), C.byref(nbytes), self.index, self._stream())
+        _lib.check(rc)
 
     def propose(self, coords, perm, split, r_first, r_count, a, seed, iteration, prop, factor):
         nall, ndim = coords.shape
@@ -75,13 +92,6 @@ def shard_bounds(ns: int, world: int, rank: int):
     r_first = min(rank * per, ns)
     r_count = max(0, min(per, ns - r_first))
     return per, r_first, r_count
-
-
-def split_permutation(nall: int, seed: int, iteration: int) -> np.ndarray:
-    """Random permutation shared by all ranks; the colour of the walker at position p is p & 1, i.e.
-    emcee's ``inds = arange(n) % 2; random.shuffle(inds)`` (RedBlueMove.propose, randomize_split=True)."""
-    rng = np.random.Generator(np.random.Philox(key=int(seed) & (2**64 - 1), counter=[0, 0, 0, int(iteration)]))
-    return rng.permutation(nall).astype(np.int32)
 
 
 class State:
@@ -173,9 +183,6 @@ class EnsembleSampler:
         self._packed_all = self._packed if self.world == 1 else torch.zeros((per * self.world, nd + 2), dtype=f64,
                                                                             device=dev)
         self._perm = torch.zeros((W,), dtype=torch.int32, device=dev)
-        self._perm_host = torch.zeros((W,), dtype=torch.int32)
-        if dev.type == "cuda":
-            self._perm_host = self._perm_host.pin_memory()
         self._steps_done = 0
 
     def _all_gather(self, out, inp):
@@ -227,8 +234,8 @@ class EnsembleSampler:
         """One stretch-move iteration: two half-steps, every walker proposed and evaluated once."""
         W = self.nwalkers
         it = self.iteration
-        self._perm_host.copy_(torch.from_numpy(split_permutation(W, self.seed, it)))
-        self._perm.copy_(self._perm_host, non_blocking=True)
+        self.ops.permutation(self._perm, self.seed, it)
+        self.aux_launches += getattr(self.ops, "launches_per_permutation", 0)
         for split in (0, 1):
             ns = (W - split + 1) // 2
             per, first, count = shard_bounds(ns, self.world, self.rank)

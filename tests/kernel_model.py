@@ -92,6 +92,14 @@ def _draws(k, seed, iteration, split, purpose):
                          np.uint32((split << 1) | purpose), np.uint32(seed & 0xFFFFFFFF), np.uint32(seed >> 32))
 
 
+def split_permutation(nall, seed, iteration):
+    """Model of jx_stretch_permutation: stable argsort of 64 Philox bits per walker.  The colour of the walker
+    at position p is p & 1, i.e. emcee's ``inds = arange(n) % 2; random.shuffle(inds)``."""
+    r0, r1, _, _ = _draws(np.arange(nall), seed, iteration, 1, 0)      # (split << 1) | purpose == 2
+    keys = (r0.astype(np.uint64) << np.uint64(32)) | r1.astype(np.uint64)
+    return np.argsort(keys, kind="stable").astype(np.int32)
+
+
 def stretch_propose(coords, perm, split, r_first, r_count, a, seed, iteration):
     nall, ndim = coords.shape
     i = np.arange(r_count)
@@ -136,6 +144,9 @@ def stretch_scatter(coords, lp, naccept, perm, split, packed_all, ns):
 class NumpyStretchOps:
     """Same interface as joxsz_b200.sampler.CudaStretchOps, on CPU torch tensors (tests only)."""
     launches_per_half_step = 3
+
+    def permutation(self, perm, seed, iteration):
+        perm.numpy()[:] = split_permutation(perm.shape[0], seed, iteration)
 
     def propose(self, coords, perm, split, r_first, r_count, a, seed, iteration, prop, factor):
         p, f = stretch_propose(coords.numpy(), perm.numpy(), split, r_first, r_count, a, seed, iteration)

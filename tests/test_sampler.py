@@ -9,7 +9,8 @@ import pytest
 import torch
 
 import kernel_model as km
-from joxsz_b200.sampler import EnsembleSampler, shard_bounds, split_permutation
+from joxsz_b200.sampler import EnsembleSampler, shard_bounds
+from kernel_model import split_permutation
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
@@ -150,6 +151,12 @@ def test_k6_kernels_match_numpy_model():
         coords = rng.normal(size=(nall, ndim))
         lp = rng.normal(size=nall)
         perm = split_permutation(nall, 5, 9)
+        perm_d = torch.zeros(nall, dtype=torch.int32, device=dev)
+        ops.permutation(perm_d, 5, 9)
+        assert np.array_equal(perm_d.cpu().numpy(), perm)
+        big = torch.zeros(65536, dtype=torch.int32, device=dev)
+        ops.permutation(big, (1 << 40) + 3, (1 << 35) + 1)
+        assert np.array_equal(big.cpu().numpy(), split_permutation(65536, (1 << 40) + 3, (1 << 35) + 1))
         seed, it = 0x1234567890ABCDEF, (1 << 33) + 17
         for split in (0, 1):
             ns = (nall - split + 1) // 2
