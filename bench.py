@@ -277,6 +277,8 @@ def run_gpu_arm(args):
         import ctypes as C
         tf = C.c_double(0.0)
         eng.lib.jx_measure_fp64_tflops(local, C.byref(tf))
+        tfd = C.c_double(0.0)
+        eng.lib.jx_measure_dmma_tflops(local, C.byref(tfd))
         flops = pk.algorithmic_flops()
         roof = {"bound": "hbm", "kernel": "k3_szmap_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
@@ -284,7 +286,7 @@ def run_gpu_arm(args):
                 "avg_launch_ms": k3_avg_s * 1e3, "launches_timed": int(k3_n),
                 "note": "algorithmic bytes = staged maps of the reference (SURVEY 8d); the kernel keeps them in shared "
                         "memory, so DRAM traffic is far below this and the binding limit is FP64 throughput",
-                "fp64": {"alg_flops_per_walker": flops["szmap"], "measured_dfma_peak_tflops": tf.value,
+                "fp64": {"alg_flops_per_walker": flops["szmap"], "measured_dfma_peak_tflops": tf.value, "measured_dmma_peak_tflops": tfd.value,
                          "achieved_tflops": flops["szmap"] * k3_walkers / k3_avg_s / 1e12 if k3_n else None}}
         stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in stages.items()}
         launches = int(sum(v[1] for v in stages.values())) + sampler.aux_launches

@@ -220,6 +220,8 @@ int jx_set_profiling(jx_handle* h, int32_t on);
 int jx_stage_times(jx_handle* h, double* ms /*[JX_NSTAGE]*/, int64_t* launches /*[JX_NSTAGE]*/);
 /* Sustained FP64 FMA throughput of the device in TFLOP/s (a dependent-chain-free DFMA loop). */
 int jx_measure_fp64_tflops(int32_t device, double* tflops);
+/* Sustained FP64 tensor-core (mma.sync.m8n8k4.f64, SASS DMMA) throughput in TFLOP/s. */
+int jx_measure_dmma_tflops(int32_t device, double* tflops);
 /* Library build info (arch, ABI). */
 const char* jx_build_info(void);
 

@@ -73,6 +73,7 @@ PROTOTYPES = {
     "jx_set_profiling": (C.c_int, [_vp, C.c_int32]),
     "jx_stage_times": (C.c_int, [_vp, _pd, C.POINTER(C.c_int64)]),
     "jx_measure_fp64_tflops": (C.c_int, [C.c_int32, _pd]),
+    "jx_measure_dmma_tflops": (C.c_int, [C.c_int32, _pd]),
     "jx_build_info": (C.c_char_p, []),
 }
 

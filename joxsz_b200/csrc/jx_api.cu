@@ -181,7 +181,15 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     UP(prior_a, s->prior_a, s->ndim);
     UP(prior_b, s->prior_b, s->ndim);
     UP(r_pp, s->r_pp, s->nr);
-    if (!rc) rc = upload_padded(h, &d.proj_op, s->proj_op, d.ncoef, s->nr, d.nrp);
+    if (!rc) rc = upload_padded(h, &d.proj_op_tap, s->proj_op, d.ncoef, s->nr, d.nrp);
+    if (!rc) {   // production layout: the 4 coefficients of a spline piece adjacent (one 32-byte entry per piece)
+        std::vector<double> il((size_t)d.ncoef * s->nr);
+        for (int p = 0; p < 4; ++p)
+            for (int g = 0; g < s->nseg; ++g)
+                memcpy(&il[((size_t)g * 4 + p) * s->nr], s->proj_op + ((size_t)p * s->nseg + g) * s->nr,
+                       sizeof(double) * s->nr);
+        rc = upload_padded(h, &d.proj_op, il.data(), d.ncoef, s->nr, d.nrp);
+    }
     if (!rc) rc = upload_padded(h, &d.y_op, s->y_op, s->nr, s->nr, d.nrp);
     UP(seg, s->seg, H * H);
     UP(dx, s->dx, H * H);
@@ -225,6 +233,34 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
         std::vector<double> t((size_t)d.hp8 * d.hp8, 0.0);
         for (int u = 0; u < H; ++u) memcpy(&t[(size_t)u * d.hp8], s->hf + (size_t)u * H, sizeof(double) * H);
         rc = upload(h, &d.hf_pad, t.data(), t.size());
+    }
+    if (!rc) {   // synthesis table: pixels with u <= v, in thread order, padded to a multiple of the CTA size
+        std::vector<jx_synth_px> t;
+        for (int u = 0; u < H; ++u)
+            for (int v = u; v < H; ++v) {
+                jx_synth_px e;
+                e.dx = s->dx[(size_t)u * H + v];
+                e.seg = (uint16_t)s->seg[(size_t)u * H + v];
+                e.u = (uint16_t)u; e.v = (uint16_t)v; e.pad = 0;
+                t.push_back(e);
+            }
+        while (t.size() % 256) { jx_synth_px e; e.dx = 0.0; e.seg = 0; e.u = 0xffff; e.v = 0; e.pad = 0; t.push_back(e); }
+        d.nsynth = (int)t.size();
+        rc = upload(h, &d.synth, t.data(), t.size());
+    }
+    if (!rc) {   // phase-D cosine matrix in mma.m8n8k4 B-fragment order: [kx tile][k step][lane]
+        const int ntile = d.hp8 / 8, nks = d.hp16 / 4;
+        std::vector<double> t((size_t)ntile * nks * 32, 0.0);
+        for (int jt = 0; jt < ntile; ++jt)
+            for (int ks = 0; ks < nks; ++ks)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int kx = jt * 8 + (lane >> 2), fk = lane & 3;
+                    const int v = 16 * (ks >> 2) + 2 * (ks & 3) + (fk & 1) + 8 * (fk >> 1);
+                    if (kx < H && v < H)
+                        t[((size_t)jt * nks + ks) * 32 + lane] =
+                            cos(2.0 * M_PI * (double)(((long long)kx * v) % s->nmap) / (double)s->nmap) * (v ? 2.0 : 1.0);
+                }
+        rc = upload(h, &d.cfrag, t.data(), t.size());
     }
     // workspace
     const size_t Wm = (size_t)s->max_walkers;
@@ -314,7 +350,7 @@ extern "C" int jx_sz_project(jx_handle* h, const double* theta, int32_t W, doubl
     jx_dev& d = h->d;
     JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     if (y) JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.y_op, d.nr, y, st));
-    if (coef) JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op, d.ncoef, coef, st));
+    if (coef) JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op_tap, d.ncoef, coef, st));
     return JX_OK;
 }
 
@@ -426,7 +462,55 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
+__global__ void dmma_peak_kernel(double* out, int iters) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 }  // namespace
+
+extern "C" int jx_measure_dmma_tflops(int32_t device, double* tflops) {
+    if (!tflops) return JX_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return JX_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 1 << 12;
+    double* buf = nullptr;
+    if (cudaMalloc(&buf, sizeof(double) * blocks * threads) != cudaSuccess) return JX_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    dmma_peak_kernel<<<blocks, threads>>>(buf, iters);   // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        dmma_peak_kernel<<<blocks, threads>>>(buf, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        // one m8n8k4 = 8*8*4 FMA = 512 flop per warp
+        double tf = 512.0 * 8.0 * (double)iters * blocks * (threads / 32) / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    cudaError_t e = cudaGetLastError();
+    *tflops = best;
+    return e == cudaSuccess ? JX_OK : JX_ERR_CUDA;
+}
 
 extern "C" int jx_measure_fp64_tflops(int32_t device, double* tflops) {
     if (!tflops) return JX_ERR_INVALID;

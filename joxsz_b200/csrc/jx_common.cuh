@@ -18,6 +18,14 @@
 constexpr int JX_WARP = 32;
 constexpr int JX_MAX_NDIM = 32;   // theta columns handled by one warp
 
+// One quarter-plane pixel of the Compton-y map, for the synthesis phase of K3: the spline piece that
+// covers its distance from the centre and the offset from that piece's left knot.  (u, v) and (v, u)
+// share the value (the map is radial), so only u <= v is stored.
+struct __align__(16) jx_synth_px {
+    double dx;
+    uint16_t seg, u, v, pad;
+};
+
 // Device-resident constants + workspace of one handle.
 struct jx_dev {
     // parameters
@@ -31,7 +39,8 @@ struct jx_dev {
     int nr, nrp /* nr rounded up to 8: leading dimension of ws_pp and the operators */, nt, nmap, nh, npad, nq, nseg,
         ncoef /* 4*nseg */;
     const double* r_pp;
-    const double* proj_op;   // [ncoef, nrp] zero padded
+    const double* proj_op;   // [ncoef, nrp] zero padded, rows interleaved [seg][4] (production layout)
+    const double* proj_op_tap; // [ncoef, nrp] rows [4][seg] as supplied (jx_sz_project's `coef` output)
     const double* y_op;      // [nr, nrp] zero padded
     const int32_t* seg;      // [nh, nh]
     const double* dx;        // [nh, nh]
@@ -45,6 +54,9 @@ struct jx_dev {
     const uint16_t* seg16;   // [nh, nh] seg narrowed
     const double* costab;    // [nmap] cos(2 pi m / nmap)
     const double* hf_pad;    // [hp8, hp8] hf zero padded
+    const jx_synth_px* synth; // [nsynth] quarter-plane pixels with u <= v, padded with u = 0xffff sentinels
+    int nsynth;               // multiple of 256
+    const double* cfrag;     // [hp8/8][hp16/4][32] w_v cos(2 pi kx v / N) in DMMA B-fragment order (K3 phase D)
     const double* w_t0;      // [nt]
     int nconv;
     const double *conv_T, *conv_I;

@@ -96,12 +96,12 @@ JX_D void dmma884(double& c0, double& c1, double a, double b) {
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// value of the Compton-y spline at quarter-plane pixel `pix` (Horner on the piece's coefficients)
-JX_D double spline_pixel(const double* __restrict__ c, int nseg, const uint16_t* __restrict__ seg16,
-                         const double* __restrict__ dx, int pix) {
-    const int s = __ldg(seg16 + pix);
-    const double t = __ldg(dx + pix);
-    return c[s] + t * (c[nseg + s] + t * (c[2 * nseg + s] + t * c[3 * nseg + s]));
+// value of the Compton-y spline on piece `s` at offset `t` from its left knot; the 4 coefficients of a
+// piece are adjacent (two 16-byte shared loads), Horner evaluation
+JX_D double spline_eval(const double* __restrict__ c, int s, double t) {
+    const double2 c01 = *reinterpret_cast<const double2*>(c + 4 * s);
+    const double2 c23 = *reinterpret_cast<const double2*>(c + 4 * s + 2);
+    return c01.x + t * (c01.y + t * (c23.x + t * c23.y));
 }
 
 // scipy interp1d(kind='linear', fill_value='extrapolate') on a small table
@@ -183,7 +183,33 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_szmap_kernel(const __grid_co
 
         double re[16], im[16];
 
-        // ================= phase A: synthesise map rows and transform them along x
+        // ================= phase A0: synthesise the quarter-plane map into xs[u, v].  The map is radial, so
+        // pixel (u, v) also fills (v, u); the table lists u <= v in thread order (one coalesced 16-byte load
+        // per pixel, all of a thread's loads in flight together).
+        {
+            constexpr int A0_UNROLL = 5;
+            const int4* tab = reinterpret_cast<const int4*>(d.synth);
+            for (int base = 0; base < d.nsynth; base += A0_UNROLL * K3_THREADS) {
+                int4 e[A0_UNROLL];
+#pragma unroll
+                for (int k = 0; k < A0_UNROLL; ++k) {
+                    const int i = base + k * K3_THREADS + tid;
+                    e[k] = i < d.nsynth ? __ldg(tab + i) : make_int4(0, 0, 0xffff0000, 0);
+                }
+#pragma unroll
+                for (int k = 0; k < A0_UNROLL; ++k) {
+                    const int sg = e[k].z & 0xffff, u = (e[k].z >> 16) & 0xffff, v = e[k].w & 0xffff;
+                    if (u != 0xffff) {
+                        const double z = spline_eval(cf, sg, __hiloint2double(e[k].y, e[k].x));
+                        xs[u * K3_XS + v] = z;
+                        xs[v * K3_XS + u] = z;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ================= phase A1: transform the rows along x, in place
         const int npair = (H + 1) >> 1;
         for (int rp = grp; rp < npair; rp += K3_GROUPS) {
             const int u0 = 2 * rp, u1 = u0 + 1;
@@ -193,8 +219,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_szmap_kernel(const __grid_co
                 const int f = fold256(t + 16 * j);
                 double vr = 0.0, vi = 0.0;
                 if (f < H) {
-                    vr = spline_pixel(cf, nseg, d.seg16, d.dx, u0 * H + f);
-                    if (has1) vi = spline_pixel(cf, nseg, d.seg16, d.dx, u1 * H + f);
+                    vr = xs[u0 * K3_XS + f];
+                    if (has1) vi = xs[u1 * K3_XS + f];
                 }
                 re[j] = vr; im[j] = vi;
             }
@@ -296,15 +322,16 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_szmap_kernel(const __grid_co
                 const int jt = item % ntile, half = item / ntile;
                 const int ut_lo = half ? nut0 : 0, ut_hi = half ? ntile : nut0;
                 const int nut = ut_hi - ut_lo;
-                const int kx = jt * 8 + frow;                    // B-fragment column of this lane
                 double acc[K3_MAXUT][2];
 #pragma unroll
                 for (int i = 0; i < K3_MAXUT; ++i) acc[i][0] = acc[i][1] = 0.0;
                 const double* arow = xs + (size_t)(ut_lo * 8 + frow) * K3_XS + voff;
-                for (int ks = 0; ks < (hp16 >> 2); ++ks) {
-                    const int v = 16 * (ks >> 2) + 2 * (ks & 3) + voff;
-                    double b = 0.0;
-                    if (kx < H && v < H) b = costab_s[(kx * v) % N] * (v ? 2.0 : 1.0);
+                const int nks = hp16 >> 2;
+                const double* bp = d.cfrag + (size_t)jt * nks * 32 + lane;     // B fragments, one coalesced load per k step
+                double bnext = __ldg(bp);
+                for (int ks = 0; ks < nks; ++ks) {
+                    const double b = bnext;
+                    if (ks + 1 < nks) bnext = __ldg(bp + (ks + 1) * 32);
                     const double* ap = arow + 16 * (ks >> 2) + 2 * (ks & 3);
 #pragma unroll
                     for (int i = 0; i < K3_MAXUT; ++i)
@@ -421,7 +448,7 @@ __global__ void k3_tap_y2d_kernel(jx_dev d, const double* coef, int W, double* y
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * N; i += gridDim.x * blockDim.x) {
         int y = i / N, x = i % N;
         int u = y < c ? c - y : y - c, v = x < c ? c - x : x - c;
-        y2d[(size_t)w * N * N + i] = spline_pixel(cf, d.nseg, d.seg16, d.dx, u * H + v);
+        y2d[(size_t)w * N * N + i] = spline_eval(cf, d.seg16[u * H + v], d.dx[u * H + v]);
     }
 }
 
