@@ -27,12 +27,11 @@
 
 namespace {
 
-constexpr int K3_THREADS = 256;
-constexpr int K3_GROUPS = K3_THREADS / 16;
+constexpr int K3_THREADS_MAX = 384;      // 24 FFT groups: 43 row pairs -> 2 rounds, 65 column pairs -> 3 rounds
+constexpr int K3_THREADS_MIN = 256;      // fallback when the larger exchange buffer does not fit
 constexpr int K3_P = 256;
 constexpr int K3_Q = K3_P / 2 + 1;       // 129
 constexpr int K3_XS = 130;               // row pitch of xs (doubles): XS/2 odd -> conflict-free column walks
-constexpr int K3_MAXUT = 9;              // u-tiles per phase-D item (H <= 129 -> 17 tiles -> 9 per half)
 
 struct k3_args {
     jx_dev d;
@@ -46,12 +45,12 @@ struct k3_smem_layout {
     size_t tw, xbuf, xs, coef, tsz, tarr, out, outp, gpart, bright, model, costab, mbar, total;
 };
 
-__host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8) {
+__host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8, int nthreads) {
     k3_smem_layout L;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~size_t(15); return at; };
     L.tw = take(256 * sizeof(double2));
-    L.xbuf = take((size_t)K3_GROUPS * JX_XB_ELEMS * sizeof(double2));
+    L.xbuf = take((size_t)(nthreads / 16) * JX_XB_ELEMS * sizeof(double2));
     L.xs = take((size_t)hp8 * K3_XS * sizeof(double));
     L.coef = take((size_t)2 * d.ncoef * sizeof(double));
     L.tsz = take((size_t)(d.nt + 1) * sizeof(double));
@@ -115,11 +114,64 @@ JX_D double linear_extrap(double x, const double* __restrict__ xk, const double*
     return slope * (x - x0) + y0;
 }
 
-__global__ void __launch_bounds__(K3_THREADS, 1) k3_szmap_kernel(const __grid_constant__ k3_args a) {
+// Phase D of the map kernel: G[kx] = sum_u hf[u, kx] sum_v conv_c[u, v] w_v cos(2 pi kx v / N) on the FP64
+// tensor cores.  Work item = (kx tile, half of the u tiles); every item runs exactly NUT u-tiles so the
+// DMMA loop carries no predicates: when the tile count is odd the second half starts one tile early and
+// leaves that tile out of the final fold.
+template <int NUT>
+JX_D void k3_phase_d(const jx_dev& d, const double* __restrict__ xs, double* __restrict__ gpart_s, int warp, int lane,
+                     int nwarps) {
+    const int hp8 = d.hp8, ntile = hp8 >> 3, nks = d.hp16 >> 2;
+    const int frow = lane >> 2, fk = lane & 3;
+    const int voff = (fk & 1) + 8 * (fk >> 1);          // k-permutation {0,1,8,9}: conflict-free fragments
+    for (int item = warp; item < 2 * ntile; item += nwarps) {
+        const int jt = item % ntile, half = item / ntile;
+        const int ut_lo = half ? ntile - NUT : 0;
+        double acc[NUT][2];
+#pragma unroll
+        for (int i = 0; i < NUT; ++i) acc[i][0] = acc[i][1] = 0.0;
+        const double* arow = xs + (size_t)(ut_lo * 8 + frow) * K3_XS + voff;
+        const double* bp = d.cfrag + (size_t)jt * nks * 32 + lane;     // B fragments, one coalesced load per k step
+        double bnext = __ldg(bp);
+        for (int ks = 0; ks < nks; ++ks) {
+            const double b = bnext;
+            if (ks + 1 < nks) bnext = __ldg(bp + (ks + 1) * 32);
+            const double* ap = arow + 16 * (ks >> 2) + 2 * (ks & 3);
+            double af[NUT];
+#pragma unroll
+            for (int i = 0; i < NUT; ++i) af[i] = ap[(size_t)i * 8 * K3_XS];
+#pragma unroll
+            for (int i = 0; i < NUT; ++i) dmma884(acc[i][0], acc[i][1], af[i], b);
+        }
+        // fold in hf[u, kx] and reduce over the 8 fragment rows
+        double g0 = 0.0, g1 = 0.0;
+        const int kc = jt * 8 + 2 * fk;
+#pragma unroll
+        for (int i = 0; i < NUT; ++i) {
+            if (half && ut_lo + i < NUT) continue;      // tile already covered by the first half (warp-uniform)
+            const double2 h = __ldg(reinterpret_cast<const double2*>(
+                d.hf_pad + (size_t)((ut_lo + i) * 8 + frow) * hp8 + kc));
+            g0 += acc[i][0] * h.x;
+            g1 += acc[i][1] * h.y;
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            g0 += __shfl_xor_sync(0xffffffffu, g0, o);
+            g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+        }
+        if (lane < 4) {
+            gpart_s[half * hp8 + kc] = g0;
+            gpart_s[half * hp8 + kc + 1] = g1;
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__ k3_args a) {
     extern __shared__ __align__(128) unsigned char k3_raw[];
     const jx_dev& d = a.d;
     const int H = d.nh, N = d.nmap, nseg = d.nseg, hp8 = d.hp8, hp16 = d.hp16;
-    const k3_smem_layout L = k3_layout(d, hp8);
+    const k3_smem_layout L = k3_layout(d, hp8, NT);
     double2* tw_s = reinterpret_cast<double2*>(k3_raw + L.tw);
     double2* xbuf_all = reinterpret_cast<double2*>(k3_raw + L.xbuf);
     double* xs = reinterpret_cast<double*>(k3_raw + L.xs);
@@ -141,9 +193,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_szmap_kernel(const __grid_co
     const uint32_t coef_bytes = (uint32_t)(d.ncoef * sizeof(double));
 
     // ---- one-time set-up of the CTA
-    for (int i = tid; i < 256; i += K3_THREADS) fft256_make_twiddle(i, tw_s[i]);
-    for (int i = tid; i < hp8 * K3_XS; i += K3_THREADS) xs[i] = 0.0;
-    for (int i = tid; i < N; i += K3_THREADS) costab_s[i] = __ldg(d.costab + i);
+    for (int i = tid; i < 256; i += NT) fft256_make_twiddle(i, tw_s[i]);
+    for (int i = tid; i < hp8 * K3_XS; i += NT) xs[i] = 0.0;
+    for (int i = tid; i < N; i += NT) costab_s[i] = __ldg(d.costab + i);
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
@@ -173,7 +225,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_szmap_kernel(const __grid_co
         }
         const bool skip = a.flags && a.flags[w] != 0u;
         if (tid < d.nt) tsz_s[tid] = a.tsz[(size_t)w * d.nt + tid];
-        for (int i = K3_THREADS + tid; i < d.nt; i += K3_THREADS) tsz_s[i] = a.tsz[(size_t)w * d.nt + i];
+        for (int i = NT + tid; i < d.nt; i += NT) tsz_s[i] = a.tsz[(size_t)w * d.nt + i];
         mbar_wait(&mbar[buf], (uint32_t)((it >> 1) & 1));
         if (skip) {                         // block-uniform
             if (tid == 0 && a.ll) a.ll[w] = jx_neg_inf();
@@ -189,11 +241,11 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_szmap_kernel(const __grid_co
         {
             constexpr int A0_UNROLL = 5;
             const int4* tab = reinterpret_cast<const int4*>(d.synth);
-            for (int base = 0; base < d.nsynth; base += A0_UNROLL * K3_THREADS) {
+            for (int base = 0; base < d.nsynth; base += A0_UNROLL * NT) {
                 int4 e[A0_UNROLL];
 #pragma unroll
                 for (int k = 0; k < A0_UNROLL; ++k) {
-                    const int i = base + k * K3_THREADS + tid;
+                    const int i = base + k * NT + tid;
                     e[k] = i < d.nsynth ? __ldg(tab + i) : make_int4(0, 0, 0xffff0000, 0);
                 }
 #pragma unroll
@@ -211,7 +263,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_szmap_kernel(const __grid_co
 
         // ================= phase A1: transform the rows along x, in place
         const int npair = (H + 1) >> 1;
-        for (int rp = grp; rp < npair; rp += K3_GROUPS) {
+        for (int rp = grp; rp < npair; rp += (NT / 16)) {
             const int u0 = 2 * rp, u1 = u0 + 1;
             const bool has1 = u1 < H;
 #pragma unroll
@@ -241,17 +293,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_szmap_kernel(const __grid_co
 
         // ================= phase B: columns -- cyclic convolution with the beam along y
         const int ncpair = (K3_Q + 1) >> 1;
-        for (int cp = grp; cp < ncpair; cp += K3_GROUPS) {
+        for (int cp = grp; cp < ncpair; cp += (NT / 16)) {
             const int kx = 2 * cp;
             const bool has1 = kx + 1 < K3_Q;
-            double2 bh[16];
-#pragma unroll
-            for (int p = 0; p < 16; ++p) {
-                const int f = fold256(t + 16 * rev16(p));
-                const double* b = d.bhat + (size_t)f * K3_Q + kx;
-                bh[p].x = __ldg(b);
-                bh[p].y = has1 ? __ldg(b + 1) : 0.0;
-            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int f = fold256(t + 16 * j);
@@ -266,8 +310,10 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_szmap_kernel(const __grid_co
             double re2[16], im2[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {           // spectrum * beam, back to natural register order
-                re2[j] = re[rev16(j)] * bh[rev16(j)].x;
-                im2[j] = im[rev16(j)] * bh[rev16(j)].y;
+                // beam spectrum of this column pair in thread order [cp][p][t]: 256 contiguous bytes per group
+                const double2 bh = __ldg(d.bhat_sw + ((size_t)cp * 16 + rev16(j)) * 16 + t);
+                re2[j] = re[rev16(j)] * bh.x;
+                im2[j] = im[rev16(j)] * bh.y;
             }
             fft256_pass1(t, re2, im2, tw_s, xbuf);
             __syncwarp(gmask);
@@ -282,7 +328,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_szmap_kernel(const __grid_co
         __syncthreads();
 
         // ================= phase C: rows back to pixel space, in place: xs[u, v] = conv_c[u, v]
-        for (int rp = grp; rp < npair; rp += K3_GROUPS) {
+        for (int rp = grp; rp < npair; rp += (NT / 16)) {
             const int u0 = 2 * rp, u1 = u0 + 1;
             const bool has1 = u1 < H;
 #pragma unroll
@@ -309,60 +355,25 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_szmap_kernel(const __grid_co
 
         if (a.convq) {
             double* cq = a.convq + (size_t)w * H * H;
-            for (int i = tid; i < H * H; i += K3_THREADS) cq[i] = xs[(i / H) * K3_XS + (i % H)];
+            for (int i = tid; i < H * H; i += NT) cq[i] = xs[(i / H) * K3_XS + (i % H)];
         }
 
         // ================= phase D: G[kx] = sum_u hf[u,kx] sum_v conv_c[u,v] w_v cos(2 pi kx v/N)   (DMMA)
-        {
-            const int ntile = hp8 >> 3;
-            const int nut0 = (ntile + 1) >> 1;
-            const int frow = lane >> 2, fk = lane & 3;
-            const int voff = (fk & 1) + 8 * (fk >> 1);          // k-permutation {0,1,8,9}: conflict-free fragments
-            for (int item = warp; item < 2 * ntile; item += K3_THREADS / 32) {
-                const int jt = item % ntile, half = item / ntile;
-                const int ut_lo = half ? nut0 : 0, ut_hi = half ? ntile : nut0;
-                const int nut = ut_hi - ut_lo;
-                double acc[K3_MAXUT][2];
-#pragma unroll
-                for (int i = 0; i < K3_MAXUT; ++i) acc[i][0] = acc[i][1] = 0.0;
-                const double* arow = xs + (size_t)(ut_lo * 8 + frow) * K3_XS + voff;
-                const int nks = hp16 >> 2;
-                const double* bp = d.cfrag + (size_t)jt * nks * 32 + lane;     // B fragments, one coalesced load per k step
-                double bnext = __ldg(bp);
-                for (int ks = 0; ks < nks; ++ks) {
-                    const double b = bnext;
-                    if (ks + 1 < nks) bnext = __ldg(bp + (ks + 1) * 32);
-                    const double* ap = arow + 16 * (ks >> 2) + 2 * (ks & 3);
-#pragma unroll
-                    for (int i = 0; i < K3_MAXUT; ++i)
-                        if (i < nut) dmma884(acc[i][0], acc[i][1], ap[(size_t)i * 8 * K3_XS], b);
-                }
-                // fold in hf[u, kx] and reduce over the 8 fragment rows
-                double g0 = 0.0, g1 = 0.0;
-                const int kc = jt * 8 + 2 * fk;
-#pragma unroll
-                for (int i = 0; i < K3_MAXUT; ++i)
-                    if (i < nut) {
-                        const double2 h = __ldg(reinterpret_cast<const double2*>(
-                            d.hf_pad + (size_t)((ut_lo + i) * 8 + frow) * hp8 + kc));
-                        g0 += acc[i][0] * h.x;
-                        g1 += acc[i][1] * h.y;
-                    }
-#pragma unroll
-                for (int o = 4; o < 32; o <<= 1) {
-                    g0 += __shfl_xor_sync(0xffffffffu, g0, o);
-                    g1 += __shfl_xor_sync(0xffffffffu, g1, o);
-                }
-                if (lane < 4) {
-                    gpart_s[half * hp8 + kc] = g0;
-                    gpart_s[half * hp8 + kc + 1] = g1;
-                }
-            }
+        switch (((hp8 >> 3) + 1) >> 1) {
+            case 1: k3_phase_d<1>(d, xs, gpart_s, warp, lane, NT / 32); break;
+            case 2: k3_phase_d<2>(d, xs, gpart_s, warp, lane, NT / 32); break;
+            case 3: k3_phase_d<3>(d, xs, gpart_s, warp, lane, NT / 32); break;
+            case 4: k3_phase_d<4>(d, xs, gpart_s, warp, lane, NT / 32); break;
+            case 5: k3_phase_d<5>(d, xs, gpart_s, warp, lane, NT / 32); break;
+            case 6: k3_phase_d<6>(d, xs, gpart_s, warp, lane, NT / 32); break;
+            case 7: k3_phase_d<7>(d, xs, gpart_s, warp, lane, NT / 32); break;
+            case 8: k3_phase_d<8>(d, xs, gpart_s, warp, lane, NT / 32); break;
+            default: k3_phase_d<9>(d, xs, gpart_s, warp, lane, NT / 32); break;
         }
         __syncthreads();
 
         // ================= phase E: row[v] = 1/N^2 sum_kx w_kx cos(2 pi kx v / N) G[kx]
-        for (int idx = tid; idx < 2 * H; idx += K3_THREADS) {
+        for (int idx = tid; idx < 2 * H; idx += NT) {
             const int v = idx % H, part = idx / H;
             double s0 = 0.0, s1 = 0.0;
             int m = (part * v) % N;                  // (kx * v) mod N, kx = part, part+2, ...
@@ -390,14 +401,14 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_szmap_kernel(const __grid_co
             s = warp_sum(s);
             if (lane == 0) tarr_s[0] = s;
         }
-        for (int i = tid; i < d.nt; i += K3_THREADS) tarr_s[i + 1] = tsz_s[i];
+        for (int i = tid; i < d.nt; i += NT) tarr_s[i + 1] = tsz_s[i];
         __syncthreads();
 
         // ================= phase F: brightness profile, model at the data radii, chi^2, total
         const int csrc = d.slot_src[JX_CALIB];
         const double calib = csrc < 0 ? d.slot_val[JX_CALIB] : a.theta[(size_t)w * d.ndim + csrc];
         const double inv_n2 = 1.0 / ((double)N * (double)N);
-        for (int v = tid; v < H; v += K3_THREADS) {
+        for (int v = tid; v < H; v += NT) {
             const double r = (outp_s[v] + outp_s[hp8 + v]) * inv_n2;
             out_s[v] = r;
             const double br = r * linear_extrap(tarr_s[v], d.conv_T, d.conv_I, d.nconv) * calib;
@@ -406,7 +417,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_szmap_kernel(const __grid_co
             if (a.bright) a.bright[(size_t)w * H + v] = br;
         }
         __syncthreads();
-        for (int dpt = warp; dpt < d.nd; dpt += K3_THREADS / 32) {
+        for (int dpt = warp; dpt < d.nd; dpt += NT / 32) {
             double s = 0.0;
             const double* g = d.g_op + (size_t)dpt * H;
             for (int i = lane; i < H; i += 32) s += __ldg(g + i) * bright_s[i];
@@ -513,12 +524,22 @@ __global__ void k3_tap_mapout_kernel(jx_dev d, const double* costab, const doubl
 
 }  // namespace
 
-cudaError_t jx_szmap_configure(const jx_dev& d) {
-    k3_smem_layout L = k3_layout(d, d.hp8);
-    return cudaFuncSetAttribute(k3_szmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+// 384 threads when its exchange buffers fit the 227 KB of shared memory a CTA can have, else 256
+static int k3_pick_threads(const jx_dev& d) {
+    return k3_layout(d, d.hp8, K3_THREADS_MAX).total <= 232448 ? K3_THREADS_MAX : K3_THREADS_MIN;
 }
 
-size_t jx_szmap_smem_bytes(const jx_dev& d) { return k3_layout(d, d.hp8).total; }
+cudaError_t jx_szmap_configure(const jx_dev& d) {
+    const int nt = k3_pick_threads(d);
+    k3_smem_layout L = k3_layout(d, d.hp8, nt);
+    if (nt == K3_THREADS_MAX)
+        return cudaFuncSetAttribute(k3_szmap_kernel<K3_THREADS_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)L.total);
+    return cudaFuncSetAttribute(k3_szmap_kernel<K3_THREADS_MIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)L.total);
+}
+
+size_t jx_szmap_smem_bytes(const jx_dev& d) { return k3_layout(d, d.hp8, k3_pick_threads(d)).total; }
 
 cudaError_t jx_launch_szmap(const jx_dev& d, const double* theta, const double* coef, const double* tsz,
                             const uint32_t* flags, const double* prior, const double* xlike, int W, int sm_count,
@@ -529,9 +550,13 @@ cudaError_t jx_launch_szmap(const jx_dev& d, const double* theta, const double* 
     a.d = d; a.theta = theta; a.coef = coef; a.tsz = tsz; a.prior = prior; a.xlike = xlike; a.flags = flags;
     a.W = W;
     a.convq = convq; a.row = row; a.bright = bright; a.model = model; a.chisq = chisq; a.ll = ll;
-    k3_smem_layout L = k3_layout(d, d.hp8);
+    const int nt = k3_pick_threads(d);
+    k3_smem_layout L = k3_layout(d, d.hp8, nt);
     int grid = W < sm_count ? W : sm_count;
-    k3_szmap_kernel<<<grid, K3_THREADS, L.total, st>>>(a);
+    if (nt == K3_THREADS_MAX)
+        k3_szmap_kernel<K3_THREADS_MAX><<<grid, K3_THREADS_MAX, L.total, st>>>(a);
+    else
+        k3_szmap_kernel<K3_THREADS_MIN><<<grid, K3_THREADS_MIN, L.total, st>>>(a);
     return cudaGetLastError();
 }
 
