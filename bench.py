@@ -288,7 +288,8 @@ def run_gpu_arm(args):
                         "memory, so DRAM traffic is far below this and the binding limit is FP64 throughput",
                 "fp64": {"alg_flops_per_walker": flops["szmap"], "measured_dfma_peak_tflops": tf.value, "measured_dmma_peak_tflops": tfd.value,
                          "achieved_tflops": flops["szmap"] * k3_walkers / k3_avg_s / 1e12 if k3_n else None}}
-        stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in stages.items()}
+        ncalls = max(k3_n, 1)
+        stage_ms = {k: (v[0] / ncalls) for k, v in stages.items()}
         launches = int(sum(v[1] for v in stages.values())) + sampler.aux_launches
         # bounded CPU baseline on this box's cores
         pool, cores = make_pool()

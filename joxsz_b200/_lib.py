@@ -10,8 +10,8 @@ import os
 
 JX_ABI_VERSION = 3
 JX_NPAR = 19
-JX_NSTAGE = 4
-STAGE_NAMES = ("profiles", "project", "szmap", "xray")
+JX_NSTAGE = 5
+STAGE_NAMES = ("profiles", "project", "szmap", "xray", "tail")
 
 # slot order of include/joxsz_b200.h `enum jx_param_slot`, keyed by the reference's parameter names
 PARAM_SLOTS = (

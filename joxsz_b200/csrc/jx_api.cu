@@ -75,13 +75,13 @@ int check_ready(jx_handle* h, const double* theta, int W) {
 void flush_stage_events(jx_handle* h) {
     if (!h->pending) return;
     cudaEventSynchronize(h->ev[JX_NSTAGE]);
-    // execution order: profiles, xray, project, szmap
-    static const int order[JX_NSTAGE] = {JX_ST_PROFILES, JX_ST_XRAY, JX_ST_PROJECT, JX_ST_SZMAP};
+    // execution order: profiles, xray, project, szmap, tail
+    static const int order[JX_NSTAGE] = {JX_ST_PROFILES, JX_ST_XRAY, JX_ST_PROJECT, JX_ST_SZMAP, JX_ST_TAIL};
     for (int i = 0; i < JX_NSTAGE; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) {
             h->stage_ms[order[i]] += ms;
-            h->stage_launches[order[i]] += 1;
+            h->stage_launches[order[i]] += (order[i] == JX_ST_TAIL) ? 2 : 1;   // tail = row GEMM + K5
         }
     }
     h->pending = false;
@@ -90,7 +90,7 @@ void flush_stage_events(jx_handle* h) {
 }  // namespace
 
 extern "C" const char* jx_build_info(void) {
-    return "libjoxsz_b200 abi=" "3" " arch=sm_100a fp64 K1=profiles K2=dmma-project K3=fft256-szmap K4=xray";
+    return "libjoxsz_b200 abi=" "3" " arch=sm_100a fp64 K1=profiles K2=dmma-project K3=fft256-szmap K4=xray K5=tail";
 }
 
 extern "C" const char* jx_last_error(const jx_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -234,6 +234,18 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
         for (int u = 0; u < H; ++u) memcpy(&t[(size_t)u * d.hp8], s->hf + (size_t)u * H, sizeof(double) * H);
         rc = upload(h, &d.hf_pad, t.data(), t.size());
     }
+    if (!rc) {
+        std::vector<double> t((size_t)H * s->nd);
+        for (int dp = 0; dp < s->nd; ++dp)
+            for (int v = 0; v < H; ++v) t[(size_t)v * s->nd + dp] = s->g_op[(size_t)dp * H + v];
+        rc = upload(h, &d.g_op_t, t.data(), t.size());
+    }
+    if (!rc) {
+        std::vector<double> t((size_t)H * d.hp8, 0.0);
+        for (int kx = 0; kx < H; ++kx)
+            for (int v = 0; v < H; ++v) t[(size_t)v * d.hp8 + kx] = s->dinv[(size_t)kx * H + v];
+        rc = upload(h, &d.dinv_t, t.data(), t.size());
+    }
     if (!rc) {   // synthesis table: pixels with u <= v, in thread order, padded to a multiple of the CTA size
         std::vector<jx_synth_px> t;
         for (int u = 0; u < H; ++u)
@@ -289,6 +301,7 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     if (!rc) rc = dev_alloc(h, &d.ws_flags, Wm);
     if (!rc) rc = dev_alloc(h, &d.ws_coef, Wm * d.ncoef);
     if (!rc) rc = dev_alloc(h, &d.ws_row, Wm * d.nh);
+    if (!rc) rc = dev_alloc(h, &d.ws_g, Wm * d.hp8);
     if (!rc) {
         size_t smem = jx_szmap_smem_bytes(d);
         if (smem > (size_t)prop.sharedMemPerBlockOptin) {
@@ -332,10 +345,13 @@ extern "C" int jx_loglike(jx_handle* h, const double* theta, int32_t W, double* 
     if (prof) JX_CUDA(h, cudaEventRecord(h->ev[2], st));
     JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op, d.ncoef, d.ws_coef, st));
     if (prof) JX_CUDA(h, cudaEventRecord(h->ev[3], st));
-    JX_CUDA(h, jx_launch_szmap(d, theta, d.ws_coef, d.ws_tsz, d.ws_flags, d.ws_prior, d.ws_xlike, W, h->sm_count,
-                               nullptr, nullptr, nullptr, nullptr, nullptr, ll, st));
+    JX_CUDA(h, jx_launch_szmap(d, d.ws_coef, d.ws_flags, W, h->sm_count, nullptr, d.ws_g, st));
+    if (prof) JX_CUDA(h, cudaEventRecord(h->ev[4], st));
+    JX_CUDA(h, jx_launch_gemm_nt(d.ws_g, d.hp8, d.dinv_t, d.hp8, d.ws_row, d.nh, W, d.nh, d.hp8, st));
+    JX_CUDA(h, jx_launch_tail(d, theta, d.ws_row, d.ws_tsz, d.ws_flags, d.ws_prior, d.ws_xlike, W, nullptr, nullptr,
+                              nullptr, ll, st));
     if (prof) {
-        JX_CUDA(h, cudaEventRecord(h->ev[4], st));
+        JX_CUDA(h, cudaEventRecord(h->ev[5], st));
         h->pending = true;
     }
     return JX_OK;
@@ -394,8 +410,7 @@ extern "C" int jx_sz_maps(jx_handle* h, const double* theta, int32_t W, double* 
     if (y2d) JX_CUDA(h, jx_launch_tap_y2d(d, d.ws_coef, W, y2d, st));
     if (conv2d || mapout) {
         if ((rc = ensure_convq(h, W))) return rc;
-        JX_CUDA(h, jx_launch_szmap(d, theta, d.ws_coef, d.ws_tsz, nullptr, nullptr, nullptr, W, h->sm_count,
-                                   d.ws_convq, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+        JX_CUDA(h, jx_launch_szmap(d, d.ws_coef, nullptr, W, h->sm_count, d.ws_convq, d.ws_g, st));
         if (conv2d) JX_CUDA(h, jx_launch_tap_expand(d, d.ws_convq, W, conv2d, st));
         if (mapout) {
             if (h->tap_scratch_walkers < (size_t)W) {
@@ -421,8 +436,11 @@ extern "C" int jx_sz_profile(jx_handle* h, const double* theta, int32_t W, doubl
     jx_dev& d = h->d;
     JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, d.ws_tsz, nullptr, nullptr, nullptr, nullptr, st));
     JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op, d.ncoef, d.ws_coef, st));
-    JX_CUDA(h, jx_launch_szmap(d, theta, d.ws_coef, d.ws_tsz, nullptr, nullptr, nullptr, W, h->sm_count, nullptr,
-                               row, bright, model, chisq, nullptr, st));
+    JX_CUDA(h, jx_launch_szmap(d, d.ws_coef, nullptr, W, h->sm_count, nullptr, d.ws_g, st));
+    JX_CUDA(h, jx_launch_gemm_nt(d.ws_g, d.hp8, d.dinv_t, d.hp8, d.ws_row, d.nh, W, d.nh, d.hp8, st));
+    JX_CUDA(h, jx_launch_tail(d, theta, d.ws_row, d.ws_tsz, nullptr, nullptr, nullptr, W, bright, model, chisq, nullptr,
+                              st));
+    if (row) JX_CUDA(h, cudaMemcpyAsync(row, d.ws_row, sizeof(double) * W * d.nh, cudaMemcpyDeviceToDevice, st));
     return JX_OK;
 }
 

@@ -63,6 +63,8 @@ struct jx_dev {
     const double *conv_T, *conv_I;
     int nd;
     const double *g_op, *flux, *flux_err;
+    const double* g_op_t;    // [nh, nd] g_op transposed (K5 reads it coalesced over the data points)
+    const double* dinv_t;    // [nh(v), hp8(kx)] dinv transposed, zero padded: row = G . dinv as an NT GEMM
     // X-ray
     int na, nb, ntab;
     const double *midpt_kpc, *projvols, *tlog, *lnrate0, *lnrate1, *cts, *srcscale, *bkgterm;
@@ -77,7 +79,8 @@ struct jx_dev {
     double* ws_xlike;   // [W]
     uint32_t* ws_flags; // [W]
     double* ws_coef;    // [W, ncoef]
-    double* ws_row;     // [W, nh]
+    double* ws_row;     // [W, nh]  map_out[N//2, N//2:]
+    double* ws_g;       // [W, hp8] G[kx] written by the map kernel
     double* ws_convq;   // tap only, allocated lazily: [W, nh, nh]
 };
 
@@ -109,12 +112,16 @@ cudaError_t jx_launch_project(const jx_dev& d, const double* pp, int W, const do
 cudaError_t jx_launch_xray(const jx_dev& d, const double* theta, const double* ne_ann, const double* tx_ann,
                            int W, double* pred, double* cash, uint32_t* flags, cudaStream_t st);
 cudaError_t jx_launch_cash(const jx_dev& d, const double* pred, int W, double* cash, cudaStream_t st);
-// production map stage: coef -> filtered row (+ optional quarter-plane convolved map), and the tail.
-// `flags` may be NULL (evaluate every walker).  ll may be NULL (taps).
-cudaError_t jx_launch_szmap(const jx_dev& d, const double* theta, const double* coef, const double* tsz,
-                            const uint32_t* flags, const double* prior, const double* xlike, int W, int sm_count,
-                            double* convq, double* row, double* bright, double* model, double* chisq, double* ll,
-                            cudaStream_t st);
+cudaError_t jx_launch_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N,
+                              int Kpad, cudaStream_t st);
+// production map stage: coef -> G[kx] (+ optional quarter-plane convolved map).  `flags` may be NULL
+// (evaluate every walker); flagged walkers are skipped.
+cudaError_t jx_launch_szmap(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
+                            double* convq, double* g, cudaStream_t st);
+// tail: row -> bright, model, chisq, ll (any output may be NULL)
+cudaError_t jx_launch_tail(const jx_dev& d, const double* theta, const double* row, const double* tsz,
+                           const uint32_t* flags, const double* prior, const double* xlike, int W, double* bright,
+                           double* model, double* chisq, double* ll, cudaStream_t st);
 cudaError_t jx_szmap_configure(const jx_dev& d);   // one-time cudaFuncSetAttribute
 cudaError_t jx_launch_tap_y2d(const jx_dev& d, const double* coef, int W, double* y2d, cudaStream_t st);
 cudaError_t jx_launch_tap_expand(const jx_dev& d, const double* convq, int W, double* conv2d, cudaStream_t st);

@@ -122,10 +122,10 @@ k2_dgemm_nt_kernel(const double* __restrict__ A, int lda, const double* __restri
 
 }  // namespace
 
-// pp: [W, ldk] (ldk = round_up(nr, 8), zero padded), op: [nout, ldk] zero padded, out: [W, nout]
-cudaError_t jx_launch_project(const jx_dev& d, const double* pp, int W, const double* op, int nout,
-                              double* out, cudaStream_t st) {
-    if (W <= 0) return cudaSuccess;
+// C[M, N] = A[M, Kpad] . B[N, Kpad]^T; lda/ldb even, A and B zero padded up to Kpad (a multiple of 8)
+cudaError_t jx_launch_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N,
+                              int Kpad, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return cudaSuccess;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k2_dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -133,8 +133,13 @@ cudaError_t jx_launch_project(const jx_dev& d, const double* pp, int W, const do
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int ldk = d.nrp;
-    dim3 grid((nout + BN - 1) / BN, (W + BM - 1) / BM);
-    k2_dgemm_nt_kernel<<<grid, K2_THREADS, K2_SMEM, st>>>(pp, ldk, op, ldk, out, nout, W, nout, ldk);
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    k2_dgemm_nt_kernel<<<grid, K2_THREADS, K2_SMEM, st>>>(A, lda, B, ldb, C, ldc, M, N, Kpad);
     return cudaGetLastError();
+}
+
+// pp: [W, ldk] (ldk = round_up(nr, 8), zero padded), op: [nout, ldk] zero padded, out: [W, nout]
+cudaError_t jx_launch_project(const jx_dev& d, const double* pp, int W, const double* op, int nout,
+                              double* out, cudaStream_t st) {
+    return jx_launch_gemm_nt(pp, d.nrp, op, d.nrp, out, nout, W, nout, d.nrp, st);
 }

@@ -16,8 +16,8 @@
 //   B  columns xs[:, kx] --FFT256--> * bhat[ky, kx] --FFT256--> xs[u, kx]            (beam, cyclic length P)
 //   C  rows    xs[u, :]  --FFT256--> conv_c[u, v]  (in place)     = fftconvolve(y_2d, beam,'same')*step^2
 //   D  G[kx] = sum_u hf[u,kx] * sum_v conv_c[u,v] w_v cos(2 pi kx v / N)      FP64 tensor cores (DMMA)
-//   E  row[v] = 1/N^2 sum_kx w_kx cos(2 pi kx v / N) G[kx]                    = map_out[N//2, N//2 + v]
-//   F  bright = row * convert([h(0), T_SZ]) * calibration; model = g_op @ bright; chi^2; log-likelihood
+// and the kernel writes G[kx] (H doubles per walker).  The remaining steps are batched over walkers outside
+// this kernel: row = G . dinv (one small DMMA GEMM, k2_project.cu) and the conversion / chi^2 tail (k5_tail.cu).
 //
 // D+E are the exact length-N circular filter (N = 171 = 9*19 for the shipped cluster, so a dense
 // cosine transform), reduced over ky analytically because only the central row is consumed.
@@ -35,14 +35,14 @@ constexpr int K3_XS = 130;               // row pitch of xs (doubles): XS/2 odd 
 
 struct k3_args {
     jx_dev d;
-    const double *theta, *coef, *tsz, *prior, *xlike;
+    const double* coef;
     const uint32_t* flags;
     int W;
-    double *convq, *row, *bright, *model, *chisq, *ll;
+    double *convq, *g;
 };
 
 struct k3_smem_layout {
-    size_t tw, xbuf, xs, coef, tsz, tarr, out, outp, gpart, bright, model, costab, mbar, total;
+    size_t tw, xbuf, xs, coef, gpart, mbar, total;
 };
 
 __host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8, int nthreads) {
@@ -53,14 +53,7 @@ __host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8, in
     L.xbuf = take((size_t)(nthreads / 16) * JX_XB_ELEMS * sizeof(double2));
     L.xs = take((size_t)hp8 * K3_XS * sizeof(double));
     L.coef = take((size_t)2 * d.ncoef * sizeof(double));
-    L.tsz = take((size_t)(d.nt + 1) * sizeof(double));
-    L.tarr = take((size_t)(d.nh + 1) * sizeof(double));
-    L.out = take((size_t)hp8 * sizeof(double));
-    L.outp = take((size_t)2 * hp8 * sizeof(double));
     L.gpart = take((size_t)2 * hp8 * sizeof(double));
-    L.bright = take((size_t)hp8 * sizeof(double));
-    L.model = take((size_t)(d.nd + 1) * sizeof(double));
-    L.costab = take((size_t)d.nmap * sizeof(double));
     L.mbar = take(2 * sizeof(uint64_t));
     L.total = o;
     return L;
@@ -103,52 +96,48 @@ JX_D double spline_eval(const double* __restrict__ c, int s, double t) {
     return c01.x + t * (c01.y + t * (c23.x + t * c23.y));
 }
 
-// scipy interp1d(kind='linear', fill_value='extrapolate') on a small table
-JX_D double linear_extrap(double x, const double* __restrict__ xk, const double* __restrict__ yk, int n) {
-    int idx = 0;
-    for (int i = 0; i < n; ++i) idx += (__ldg(xk + i) < x) ? 1 : 0;    // searchsorted(side='left')
-    if (x != x) idx = n;
-    idx = idx < 1 ? 1 : (idx > n - 1 ? n - 1 : idx);
-    double x0 = __ldg(xk + idx - 1), x1 = __ldg(xk + idx), y0 = __ldg(yk + idx - 1), y1 = __ldg(yk + idx);
-    double slope = (y1 - y0) / (x1 - x0);
-    return slope * (x - x0) + y0;
-}
-
 // Phase D of the map kernel: G[kx] = sum_u hf[u, kx] sum_v conv_c[u, v] w_v cos(2 pi kx v / N) on the FP64
-// tensor cores.  Work item = (kx tile, half of the u tiles); every item runs exactly NUT u-tiles so the
-// DMMA loop carries no predicates: when the tile count is odd the second half starts one tile early and
-// leaves that tile out of the final fold.
+// tensor cores.  Work item = (kx tile, part of the u tiles); NSPLIT = 1 when there are at least as many
+// warps as kx tiles (one item holds every u tile: the cosine fragments are loaded once), else 2.  Every
+// item runs exactly NUT u-tiles so the DMMA loop carries no predicates: with NSPLIT = 2 and an odd tile
+// count the second part starts one tile early and leaves that tile out of the final fold.  The cosine
+// fragments come from L2 (d.cfrag, fragment order) through a 4-deep register prefetch queue.
 template <int NUT>
 JX_D void k3_phase_d(const jx_dev& d, const double* __restrict__ xs, double* __restrict__ gpart_s, int warp, int lane,
-                     int nwarps) {
-    const int hp8 = d.hp8, ntile = hp8 >> 3, nks = d.hp16 >> 2;
+                     int nwarps, int nsplit) {
+    const int hp8 = d.hp8, ntile = hp8 >> 3, nks = d.hp16 >> 2;      // nks is a multiple of 4
     const int frow = lane >> 2, fk = lane & 3;
     const int voff = (fk & 1) + 8 * (fk >> 1);          // k-permutation {0,1,8,9}: conflict-free fragments
-    for (int item = warp; item < 2 * ntile; item += nwarps) {
-        const int jt = item % ntile, half = item / ntile;
-        const int ut_lo = half ? ntile - NUT : 0;
+    for (int item = warp; item < nsplit * ntile; item += nwarps) {
+        const int jt = item % ntile, part = item / ntile;
+        const int ut_lo = part ? ntile - NUT : 0;
         double acc[NUT][2];
 #pragma unroll
         for (int i = 0; i < NUT; ++i) acc[i][0] = acc[i][1] = 0.0;
         const double* arow = xs + (size_t)(ut_lo * 8 + frow) * K3_XS + voff;
         const double* bp = d.cfrag + (size_t)jt * nks * 32 + lane;     // B fragments, one coalesced load per k step
-        double bnext = __ldg(bp);
-        for (int ks = 0; ks < nks; ++ks) {
-            const double b = bnext;
-            if (ks + 1 < nks) bnext = __ldg(bp + (ks + 1) * 32);
-            const double* ap = arow + 16 * (ks >> 2) + 2 * (ks & 3);
-            double af[NUT];
+        double bq[4];
 #pragma unroll
-            for (int i = 0; i < NUT; ++i) af[i] = ap[(size_t)i * 8 * K3_XS];
+        for (int q = 0; q < 4; ++q) bq[q] = __ldg(bp + q * 32);
+        for (int ks0 = 0; ks0 < nks; ks0 += 4) {
 #pragma unroll
-            for (int i = 0; i < NUT; ++i) dmma884(acc[i][0], acc[i][1], af[i], b);
+            for (int q = 0; q < 4; ++q) {
+                const double b = bq[q];
+                if (ks0 + 4 < nks) bq[q] = __ldg(bp + (ks0 + 4 + q) * 32);
+                const double* ap = arow + 4 * ks0 + 2 * q;             // 16 (ks >> 2) + 2 (ks & 3), ks = ks0 + q
+                double af[NUT];
+#pragma unroll
+                for (int i = 0; i < NUT; ++i) af[i] = ap[(size_t)i * 8 * K3_XS];
+#pragma unroll
+                for (int i = 0; i < NUT; ++i) dmma884(acc[i][0], acc[i][1], af[i], b);
+            }
         }
         // fold in hf[u, kx] and reduce over the 8 fragment rows
         double g0 = 0.0, g1 = 0.0;
         const int kc = jt * 8 + 2 * fk;
 #pragma unroll
         for (int i = 0; i < NUT; ++i) {
-            if (half && ut_lo + i < NUT) continue;      // tile already covered by the first half (warp-uniform)
+            if (part && ut_lo + i < NUT) continue;      // tile already covered by the first part (warp-uniform)
             const double2 h = __ldg(reinterpret_cast<const double2*>(
                 d.hf_pad + (size_t)((ut_lo + i) * 8 + frow) * hp8 + kc));
             g0 += acc[i][0] * h.x;
@@ -160,8 +149,8 @@ JX_D void k3_phase_d(const jx_dev& d, const double* __restrict__ xs, double* __r
             g1 += __shfl_xor_sync(0xffffffffu, g1, o);
         }
         if (lane < 4) {
-            gpart_s[half * hp8 + kc] = g0;
-            gpart_s[half * hp8 + kc + 1] = g1;
+            gpart_s[part * hp8 + kc] = g0;
+            gpart_s[part * hp8 + kc + 1] = g1;
         }
     }
 }
@@ -170,20 +159,13 @@ template <int NT>
 __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__ k3_args a) {
     extern __shared__ __align__(128) unsigned char k3_raw[];
     const jx_dev& d = a.d;
-    const int H = d.nh, N = d.nmap, nseg = d.nseg, hp8 = d.hp8, hp16 = d.hp16;
+    const int H = d.nh, hp8 = d.hp8, hp16 = d.hp16;
     const k3_smem_layout L = k3_layout(d, hp8, NT);
     double2* tw_s = reinterpret_cast<double2*>(k3_raw + L.tw);
     double2* xbuf_all = reinterpret_cast<double2*>(k3_raw + L.xbuf);
     double* xs = reinterpret_cast<double*>(k3_raw + L.xs);
     double* coef_s = reinterpret_cast<double*>(k3_raw + L.coef);
-    double* tsz_s = reinterpret_cast<double*>(k3_raw + L.tsz);
-    double* tarr_s = reinterpret_cast<double*>(k3_raw + L.tarr);
-    double* out_s = reinterpret_cast<double*>(k3_raw + L.out);
-    double* outp_s = reinterpret_cast<double*>(k3_raw + L.outp);
     double* gpart_s = reinterpret_cast<double*>(k3_raw + L.gpart);
-    double* bright_s = reinterpret_cast<double*>(k3_raw + L.bright);
-    double* model_s = reinterpret_cast<double*>(k3_raw + L.model);
-    double* costab_s = reinterpret_cast<double*>(k3_raw + L.costab);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(k3_raw + L.mbar);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -195,7 +177,6 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
     // ---- one-time set-up of the CTA
     for (int i = tid; i < 256; i += NT) fft256_make_twiddle(i, tw_s[i]);
     for (int i = tid; i < hp8 * K3_XS; i += NT) xs[i] = 0.0;
-    for (int i = tid; i < N; i += NT) costab_s[i] = __ldg(d.costab + i);
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
@@ -224,12 +205,9 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
             }
         }
         const bool skip = a.flags && a.flags[w] != 0u;
-        if (tid < d.nt) tsz_s[tid] = a.tsz[(size_t)w * d.nt + tid];
-        for (int i = NT + tid; i < d.nt; i += NT) tsz_s[i] = a.tsz[(size_t)w * d.nt + i];
         mbar_wait(&mbar[buf], (uint32_t)((it >> 1) & 1));
-        if (skip) {                         // block-uniform
-            if (tid == 0 && a.ll) a.ll[w] = jx_neg_inf();
-            __syncthreads();                // tsz_s reuse
+        if (skip) {                         // block-uniform: the tail kernel writes -inf for flagged walkers
+            __syncthreads();                // nobody still polls this mbarrier when thread 0 re-arms it
             continue;
         }
 
@@ -359,93 +337,21 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
         }
 
         // ================= phase D: G[kx] = sum_u hf[u,kx] sum_v conv_c[u,v] w_v cos(2 pi kx v/N)   (DMMA)
-        switch (((hp8 >> 3) + 1) >> 1) {
-            case 1: k3_phase_d<1>(d, xs, gpart_s, warp, lane, NT / 32); break;
-            case 2: k3_phase_d<2>(d, xs, gpart_s, warp, lane, NT / 32); break;
-            case 3: k3_phase_d<3>(d, xs, gpart_s, warp, lane, NT / 32); break;
-            case 4: k3_phase_d<4>(d, xs, gpart_s, warp, lane, NT / 32); break;
-            case 5: k3_phase_d<5>(d, xs, gpart_s, warp, lane, NT / 32); break;
-            case 6: k3_phase_d<6>(d, xs, gpart_s, warp, lane, NT / 32); break;
-            case 7: k3_phase_d<7>(d, xs, gpart_s, warp, lane, NT / 32); break;
-            case 8: k3_phase_d<8>(d, xs, gpart_s, warp, lane, NT / 32); break;
-            default: k3_phase_d<9>(d, xs, gpart_s, warp, lane, NT / 32); break;
-        }
-        __syncthreads();
-
-        // ================= phase E: row[v] = 1/N^2 sum_kx w_kx cos(2 pi kx v / N) G[kx]
-        for (int idx = tid; idx < 2 * H; idx += NT) {
-            const int v = idx % H, part = idx / H;
-            double s0 = 0.0, s1 = 0.0;
-            int m = (part * v) % N;                  // (kx * v) mod N, kx = part, part+2, ...
-            const int step = (2 * v) % N;
-            int kx = part;
-            for (; kx + 2 < H; kx += 4) {
-                double g = gpart_s[kx] + gpart_s[hp8 + kx];
-                s0 += costab_s[m] * (kx ? 2.0 : 1.0) * g;
-                m += step; if (m >= N) m -= N;
-                double g2 = gpart_s[kx + 2] + gpart_s[hp8 + kx + 2];
-                s1 += costab_s[m] * 2.0 * g2;
-                m += step; if (m >= N) m -= N;
+        {
+            const int ntile = hp8 >> 3, nwarps = NT / 32;
+            const int nsplit = ntile <= nwarps ? 1 : 2;
+            switch ((ntile + nsplit - 1) / nsplit) {
+#define JX_D_CASE(n) case n: k3_phase_d<n>(d, xs, gpart_s, warp, lane, nwarps, nsplit); break;
+                JX_D_CASE(1) JX_D_CASE(2) JX_D_CASE(3) JX_D_CASE(4) JX_D_CASE(5) JX_D_CASE(6)
+                JX_D_CASE(7) JX_D_CASE(8) JX_D_CASE(9) JX_D_CASE(10) JX_D_CASE(11)
+                default: k3_phase_d<12>(d, xs, gpart_s, warp, lane, nwarps, nsplit); break;
+#undef JX_D_CASE
             }
-            for (; kx < H; kx += 2) {
-                double g = gpart_s[kx] + gpart_s[hp8 + kx];
-                s0 += costab_s[m] * (kx ? 2.0 : 1.0) * g;
-                m += step; if (m >= N) m -= N;
-            }
-            outp_s[part * hp8 + v] = s0 + s1;
+            __syncthreads();
+            // G[kx] leaves the kernel; row = G . dinv and the tail are batched over walkers afterwards
+            if (tid < hp8) a.g[(size_t)w * hp8 + tid] = nsplit == 1 ? gpart_s[tid] : gpart_s[tid] + gpart_s[hp8 + tid];
         }
-        // h(0) = w_t0 . t_prof  (warp 7 while the others finish phase E)
-        if (warp == 7) {
-            double s = 0.0;
-            for (int i = lane; i < d.nt; i += 32) s += __ldg(d.w_t0 + i) * tsz_s[i];
-            s = warp_sum(s);
-            if (lane == 0) tarr_s[0] = s;
-        }
-        for (int i = tid; i < d.nt; i += NT) tarr_s[i + 1] = tsz_s[i];
-        __syncthreads();
-
-        // ================= phase F: brightness profile, model at the data radii, chi^2, total
-        const int csrc = d.slot_src[JX_CALIB];
-        const double calib = csrc < 0 ? d.slot_val[JX_CALIB] : a.theta[(size_t)w * d.ndim + csrc];
-        const double inv_n2 = 1.0 / ((double)N * (double)N);
-        for (int v = tid; v < H; v += NT) {
-            const double r = (outp_s[v] + outp_s[hp8 + v]) * inv_n2;
-            out_s[v] = r;
-            const double br = r * linear_extrap(tarr_s[v], d.conv_T, d.conv_I, d.nconv) * calib;
-            bright_s[v] = br;
-            if (a.row) a.row[(size_t)w * H + v] = r;
-            if (a.bright) a.bright[(size_t)w * H + v] = br;
-        }
-        __syncthreads();
-        for (int dpt = warp; dpt < d.nd; dpt += NT / 32) {
-            double s = 0.0;
-            const double* g = d.g_op + (size_t)dpt * H;
-            for (int i = lane; i < H; i += 32) s += __ldg(g + i) * bright_s[i];
-            s = warp_sum(s);
-            if (lane == 0) {
-                model_s[dpt] = s;
-                if (a.model) a.model[(size_t)w * d.nd + dpt] = s;
-            }
-        }
-        __syncthreads();
-        if (warp == 0) {
-            double c = 0.0;
-            for (int i = lane; i < d.nd; i += 32) {
-                double z = (__ldg(d.flux + i) - model_s[i]) / __ldg(d.flux_err + i);
-                z = z * z;
-                if (z == z) c += z;                 // np.nansum drops NaN terms
-            }
-            c = warp_sum(c);
-            if (lane == 0) {
-                if (a.chisq) a.chisq[w] = c;
-                if (a.ll) {
-                    const double xl = a.xlike ? a.xlike[w] : 0.0;
-                    const double pr = a.prior ? a.prior[w] : 0.0;
-                    a.ll[w] = (xl + pr) + (-c / 2.0);
-                }
-            }
-        }
-        __syncthreads();
+        // the next iteration's first barrier orders these reads of gpart_s / xs before they are rewritten
     }
 }
 
@@ -541,15 +447,11 @@ cudaError_t jx_szmap_configure(const jx_dev& d) {
 
 size_t jx_szmap_smem_bytes(const jx_dev& d) { return k3_layout(d, d.hp8, k3_pick_threads(d)).total; }
 
-cudaError_t jx_launch_szmap(const jx_dev& d, const double* theta, const double* coef, const double* tsz,
-                            const uint32_t* flags, const double* prior, const double* xlike, int W, int sm_count,
-                            double* convq, double* row, double* bright, double* model, double* chisq, double* ll,
-                            cudaStream_t st) {
+cudaError_t jx_launch_szmap(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
+                            double* convq, double* g, cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
     k3_args a;
-    a.d = d; a.theta = theta; a.coef = coef; a.tsz = tsz; a.prior = prior; a.xlike = xlike; a.flags = flags;
-    a.W = W;
-    a.convq = convq; a.row = row; a.bright = bright; a.model = model; a.chisq = chisq; a.ll = ll;
+    a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.g = g;
     const int nt = k3_pick_threads(d);
     k3_smem_layout L = k3_layout(d, d.hp8, nt);
     int grid = W < sm_count ? W : sm_count;
