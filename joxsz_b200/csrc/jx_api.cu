@@ -235,6 +235,16 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
         rc = upload(h, &d.hf_pad, t.data(), t.size());
     }
     if (!rc) {
+        std::vector<double> t(s->nr);
+        for (int i = 0; i < s->nr; ++i) t[i] = log(s->r_pp[i]);
+        rc = upload(h, &d.ln_r_pp, t.data(), t.size());
+    }
+    if (!rc) {
+        std::vector<double> t(s->na);
+        for (int i = 0; i < s->na; ++i) t[i] = log(s->midpt_kpc[i]);
+        rc = upload(h, &d.ln_midpt, t.data(), t.size());
+    }
+    if (!rc) {
         std::vector<double> t((size_t)H * s->nd);
         for (int dp = 0; dp < s->nd; ++dp)
             for (int v = 0; v < H; ++v) t[(size_t)v * s->nd + dp] = s->g_op[(size_t)dp * H + v];

@@ -39,6 +39,7 @@ struct jx_dev {
     int nr, nrp /* nr rounded up to 8: leading dimension of ws_pp and the operators */, nt, nmap, nh, npad, nq, nseg,
         ncoef /* 4*nseg */;
     const double* r_pp;
+    const double *ln_r_pp, *ln_midpt;   // natural logs of r_pp / midpt_kpc (derived at jx_create)
     const double* proj_op;   // [ncoef, nrp] zero padded, rows interleaved [seg][4] (production layout)
     const double* proj_op_tap; // [ncoef, nrp] rows [4][seg] as supplied (jx_sz_project's `coef` output)
     const double* y_op;      // [nr, nrp] zero padded

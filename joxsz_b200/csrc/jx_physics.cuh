@@ -13,23 +13,29 @@ constexpr double JX_G_CGS = 6.67428e-8;
 constexpr double JX_SOLAR_MASS_G = 1.989e33;
 
 // Per-walker quantities that do not depend on radius, hoisted out of the radial loop.
+//
+// The radial formulas are evaluated in the log domain: with ln r tabulated once per grid and ln r_p,
+// ln r_c, ln r_s taken once per walker, every power of the reference's expressions becomes part of one
+// exponent, so a radius costs 4 exp + 3 log instead of 8 pow.  Differences from numpy's pow-by-pow
+// evaluation are a few 1e-16 times the size of the exponent (<= ~30 here), far inside the 1e-12
+// agreement the parity tests assert on the profiles.
 struct jx_walker_pars {
     double P0, a, b, c, rp;
-    double n0sq, beta, rc, rs, alpha, eps, gamma;
+    double n0, n0sq, beta, rc, rs, alpha, eps, gamma;
     double n02sq, beta2, rc2;
     double tratio;           // 10**log(T_X/T_SZ)
     double e_press;          // (b-c)/a
-    double e_dpress;         // (b-c+a)/a
     double e_core;           // 3 beta - alpha/2
     double e_outer;          // eps/gamma
+    double ln_rp, ln_rc, ln_rs, ln_rc2;
     int dens_double;
 };
 
 JX_HD jx_walker_pars jx_prepare(const double* p, int dens_mode) {
     jx_walker_pars w;
     w.P0 = p[JX_P0]; w.a = p[JX_A]; w.b = p[JX_B]; w.c = p[JX_C]; w.rp = p[JX_RP];
-    double n0 = pow(10.0, p[JX_LOGN0]);
-    w.n0sq = n0 * n0;
+    w.n0 = pow(10.0, p[JX_LOGN0]);
+    w.n0sq = w.n0 * w.n0;
     w.beta = p[JX_BETA];
     w.rc = pow(10.0, p[JX_LOGRC]);
     w.rs = pow(10.0, p[JX_LOGRS]);
@@ -45,38 +51,37 @@ JX_HD jx_walker_pars jx_prepare(const double* p, int dens_mode) {
     }
     w.tratio = pow(10.0, p[JX_LOGTRATIO]);
     w.e_press = (w.b - w.c) / w.a;
-    w.e_dpress = (w.b - w.c + w.a) / w.a;
     w.e_core = 3.0 * w.beta - w.alpha / 2.0;
     w.e_outer = w.eps / w.gamma;
+    w.ln_rp = log(w.rp); w.ln_rc = log(w.rc); w.ln_rs = log(w.rs); w.ln_rc2 = log(w.rc2);
     return w;
 }
 
-// P(r) and dP/dr.  x^c, x^a and (1+x^a) are shared between the two, exactly the factors the
-// reference raises to powers (joxsz_funcs.py:287, 301).
-JX_HD void jx_pressure(const jx_walker_pars& w, double r, double& press, double& dpress) {
-    double x = r / w.rp;
-    double xc = pow(x, w.c);
-    double xa = pow(x, w.a);
-    double opa = 1.0 + xa;
-    press = w.P0 / (xc * pow(opa, w.e_press));
-    dpress = -w.P0 * (w.c + w.b * xa) / (w.rp * pow(x, w.c + 1.0) * pow(opa, w.e_dpress));
+// P(r) and dP/dr at radius r (lr = ln r).  With x = r/r_p:
+//   P  = P0 / (x^c (1+x^a)^((b-c)/a))                                   (joxsz_funcs.py:287)
+//   P' = -P0 (c + b x^a) / (r_p x^(c+1) (1+x^a)^((b-c+a)/a)) = -(c + b x^a) P / (r (1+x^a))   (:301)
+JX_HD void jx_pressure(const jx_walker_pars& w, double r, double lr, double& press, double& dpress) {
+    const double lx = lr - w.ln_rp;
+    const double xa = exp(w.a * lx);
+    const double opa = 1.0 + xa;
+    press = w.P0 * exp(-(w.c * lx + w.e_press * log(opa)));
+    dpress = -(w.c + w.b * xa) * press / (r * opa);
 }
 
-JX_HD double jx_pressure_only(const jx_walker_pars& w, double r) {
-    double x = r / w.rp;
-    return w.P0 / (pow(x, w.c) * pow(1.0 + pow(x, w.a), w.e_press));
+JX_HD double jx_pressure_only(const jx_walker_pars& w, double lr) {
+    const double lx = lr - w.ln_rp;
+    return w.P0 * exp(-(w.c * lx + w.e_press * log(1.0 + exp(w.a * lx))));
 }
 
-// n_e(r) (joxsz_funcs.py:389-395)
-JX_HD double jx_density(const jx_walker_pars& w, double r) {
-    double x = r / w.rc;
-    double res = w.n0sq * pow(x, -w.alpha)
-                 / (pow(1.0 + x * x, w.e_core) * pow(1.0 + pow(r / w.rs, w.gamma), w.e_outer));
-    if (w.dens_double) {
-        double x2 = r / w.rc2;
-        res += w.n02sq / pow(1.0 + x2 * x2, 3.0 * w.beta2);
-    }
-    return sqrt(res);
+// n_e(r) (joxsz_funcs.py:389-395): sqrt(n0^2 x^-alpha / ((1+x^2)^(3 beta - alpha/2) (1+(r/rs)^gamma)^(eps/gamma)) [+ 2nd beta model])
+JX_HD double jx_density(const jx_walker_pars& w, double lr) {
+    const double lxc = lr - w.ln_rc;
+    const double x2 = exp(2.0 * lxc);
+    const double t3 = exp(w.gamma * (lr - w.ln_rs));
+    const double ex = -(w.alpha * lxc + w.e_core * log(1.0 + x2) + w.e_outer * log(1.0 + t3));
+    if (!w.dens_double) return w.n0 * exp(0.5 * ex);
+    const double y2 = exp(2.0 * (lr - w.ln_rc2));
+    return sqrt(w.n0sq * exp(ex) + w.n02sq * exp(-3.0 * w.beta2 * log(1.0 + y2)));
 }
 
 // M(<r) in solar masses (joxsz_funcs.py:433-437)

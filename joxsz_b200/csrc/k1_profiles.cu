@@ -58,10 +58,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_profiles_kernel(const __grid
 
     // ---- radial grid: pressure, T_SZ, mass
     for (int i = lane; i < d.nr; i += 32) {
-        double r = __ldg(d.r_pp + i);
+        const double r = __ldg(d.r_pp + i), lr = __ldg(d.ln_r_pp + i);
         double p, dp;
-        jx_pressure(wp, r, p, dp);
-        double ne = jx_density(wp, r);
+        jx_pressure(wp, r, lr, p, dp);
+        const double ne = jx_density(wp, lr);
         if (a.pp) a.pp[(size_t)w * a.ld_pp + i] = p;
         if (a.tsz && i < d.nt) a.tsz[(size_t)w * d.nt + i] = p / ne;
         mass_s[i] = jx_mass(dp, ne, r, 0.61);
@@ -84,9 +84,9 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_profiles_kernel(const __grid
 
     // ---- annulus mid-points: n_e and T_X
     for (int i = lane; i < d.na; i += 32) {
-        double r = __ldg(d.midpt_kpc + i);
-        double ne = jx_density(wp, r);
-        double tsz = jx_pressure_only(wp, r) / ne;
+        const double lr = __ldg(d.ln_midpt + i);
+        const double ne = jx_density(wp, lr);
+        const double tsz = jx_pressure_only(wp, lr) / ne;
         if (a.ne_ann) a.ne_ann[(size_t)w * d.na + i] = ne;
         if (a.tx_ann) a.tx_ann[(size_t)w * d.na + i] = tsz * wp.tratio;
     }
@@ -112,14 +112,14 @@ __global__ void __launch_bounds__(256) k_radial_kernel(const __grid_constant__ k
     __syncthreads();
     const jx_walker_pars wp = wp_s;
     for (int i = threadIdx.x; i < a.n; i += blockDim.x) {
-        double r = a.r[i];
+        const double r = a.r[i], lr = log(r);
         size_t o = (size_t)w * a.n + i;
         double p, dp;
-        jx_pressure(wp, r, p, dp);
+        jx_pressure(wp, r, lr, p, dp);
         if (a.press) a.press[o] = p;
         if (a.dpress) a.dpress[o] = dp;
         if (a.ne || a.tsz || a.tx || a.mass) {
-            double ne = jx_density(wp, r);
+            double ne = jx_density(wp, lr);
             if (a.ne) a.ne[o] = ne;
             if (a.tsz) a.tsz[o] = p / ne;
             if (a.tx) a.tx[o] = (p / ne) * wp.tratio;
