@@ -249,11 +249,15 @@ def run_gpu_arm(args):
     for _ in range(2):
         eng(host_theta)
     barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    e0.record()
     for _ in range(args.steps):
-        out = eng(host_theta)
+        out = eng(host_theta)          # numpy in (pinned staging + H2D), kernels, D2H, numpy out -- every step
+    e1.record()
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_wall_s = time.perf_counter() - t0
+    e2e_s = max(e0.elapsed_time(e1) * 1e-3, e2e_wall_s)      # device clock; the host clock can only be longer
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -290,10 +294,32 @@ def run_gpu_arm(args):
                          "achieved_tflops": flops["szmap"] * k3_walkers / k3_avg_s / 1e12 if k3_n else None}}
         ncalls = max(k3_n, 1)
         stage_ms = {k: (v[0] / ncalls) for k, v in stages.items()}
+        # DRAM traffic of the dominant kernel from the committed ncu capture of this same command (per launch)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "k3_ncu_traffic.json")))
+            roof["traffic"] = tr["dram_bytes_per_launch"] * (k3_walkers / tr["walkers_per_launch"])
+            roof["traffic_source"] = tr.get("source")
+        except Exception:
+            pass
+        # every stage against the roofline north_star names for it: HBM for profiles / map / reduction,
+        # FP64 tensor (DMMA) peak for the projection GEMM.  Algorithmic figures: SURVEY.md 8(d), DESIGN.md 5.
+        nw = k3_walkers
+        def hbm(stage, key):
+            t_s = stage_ms[stage] * 1e-3
+            gbs = alg[key] * nw / t_s / 1e9 if t_s > 0 else None
+            return {"bound": "hbm", "alg_bytes_per_walker": alg[key], "ms": stage_ms[stage], "achieved_gbs": gbs,
+                    "frac_of_measured_hbm": gbs / hbm_peak if gbs else None}
+        proj_tf = flops["project"] * nw / (stage_ms["project"] * 1e-3) / 1e12 if stage_ms["project"] > 0 else None
+        stage_roof = {"profiles": hbm("profiles", "profiles"), "szmap": hbm("szmap", "szmap"),
+                      "xray": hbm("xray", "xray"), "tail": hbm("tail", "tail"),
+                      "project": {"bound": "tensor(fp64 dmma)", "alg_flops_per_walker": flops["project"],
+                                  "ms": stage_ms["project"], "achieved_tflops": proj_tf,
+                                  "peak_tflops_measured_dmma": tfd.value,
+                                  "frac": proj_tf / tfd.value if proj_tf and tfd.value else None}}
         launches = int(sum(v[1] for v in stages.values())) + sampler.aux_launches
         # bounded CPU baseline on this box's cores
         pool, cores = make_pool()
-        sample_n = max(cores * 32, 256)
+        sample_n = max(cores * 64, 512)
         cpu_rate, cpu_dt, cpu_ll = cpu_reference_rate(host_theta[:sample_n], pool)
         pool.close()
         gpu_ll = eng(host_theta[:sample_n])
@@ -311,6 +337,7 @@ def run_gpu_arm(args):
                 "gpu_launches": launches,
                 "roofline": roof,
                 "stage_ms_per_launch": stage_ms,
+                "stage_rooflines": stage_roof,
                 "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
                                  "sample": f"{sample_n} walkers of the same ensemble, literal per-walker oracle path, "
                                            f"Pool({cores}), {cpu_dt:.1f} s"},

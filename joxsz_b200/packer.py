@@ -248,6 +248,7 @@ class PackedSetup:
             "project": s * (nr + 4 * self.map_ops.nseg),
             "szmap": s * (nr + 3 * N * N + H),
             "xray": s * (3 * self.na + self.nb * self.na),
+            "tail": s * (H + self.nb * self.na + 1),
         }
 
     def algorithmic_flops(self):
@@ -255,6 +256,6 @@ class PackedSetup:
         pd = self.map_ops.P
         lg = math.log2
         return {
-            "project": 2.0 * nr * nr,
+            "project": 2.0 * nr * 4 * self.map_ops.nseg,
             "szmap": 2 * 5 * pd * pd * lg(pd * pd) + 2 * 5 * N * N * lg(N * N) + 6 * pd * pd + 6 * N * N,
         }
