@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define JX_ABI_VERSION 3
+#define JX_ABI_VERSION 4
 
 typedef enum jx_status {
     JX_OK = 0,
@@ -114,6 +114,11 @@ typedef struct jx_setup {
     const double*  g_op;             /* [nd, H] spline through (radius[sep:], prof) evaluated at the data radii */
     const double*  flux;             /* [nd] */
     const double*  flux_err;         /* [nd] */
+    /* -- optional integrated-Compton-parameter penalty (joxsz_funcs.py:480-487, `calc_integ`, joxsz_main.py:65) */
+    int32_t calc_integ;              /* 0 = off (reference default) */
+    const double*  w_integ;          /* [nr] cint = w_integ . pressure  (Simpson weights * 2 pi * y scaling * Abel), may be
+                                        NULL when calc_integ == 0 */
+    double integ_mu, integ_sig;      /* Gaussian penalty -((cint - mu) / sig)^2 / 2 */
 
     /* -- X-ray (mbproj2 Annuli / Band / CountRate; joxsz_funcs.py:184-211, 495-505) */
     int32_t na;                      /* annuli = shells */
@@ -160,9 +165,10 @@ int jx_sz_maps(jx_handle* h, const double* theta, int32_t W,
                double* y2d, double* conv2d, double* mapout, void* stream);
 
 /* K3+K5: filtered row map_out[N//2, N//2:] [W,H]; `get_sz_like('bright')` [W,H] (:472-473);
- * model at the data radii [W,nd] (:476); chisq [W] (:478). */
+ * model at the data radii [W,nd] (:476); chisq [W] (:478); integrated Compton parameter cint [W] (:481-483,
+ * `get_sz_like('integ')`; computed whether or not calc_integ is set). */
 int jx_sz_profile(jx_handle* h, const double* theta, int32_t W,
-                  double* row, double* bright, double* model, double* chisq, void* stream);
+                  double* row, double* bright, double* model, double* chisq, double* cint, void* stream);
 
 /* K4: predicted X-ray profiles (`Fit.calcProfiles`, :527) [W,nb,na] and the Cash log-likelihood
  * (`mylikeFromProfs`, :495-505; -inf where a profile is not > 0, :529-532) [W]. */

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-JX_ABI_VERSION = 3
+JX_ABI_VERSION = 4
 JX_NPAR = 19
 JX_NSTAGE = 5
 STAGE_NAMES = ("profiles", "project", "szmap", "xray", "tail")
@@ -40,6 +40,7 @@ class JxSetup(C.Structure):
         ("cmat", _pd), ("hf", _pd), ("dinv", _pd), ("filt_q", _pd),
         ("w_t0", _pd), ("nconv", C.c_int32), ("conv_T", _pd), ("conv_I", _pd),
         ("nd", C.c_int32), ("g_op", _pd), ("flux", _pd), ("flux_err", _pd),
+        ("calc_integ", C.c_int32), ("w_integ", _pd), ("integ_mu", C.c_double), ("integ_sig", C.c_double),
         ("na", C.c_int32), ("nb", C.c_int32), ("ntab", C.c_int32),
         ("midpt_kpc", _pd), ("projvols", _pd), ("tlog", _pd),
         ("tmin", C.c_double), ("tmax", C.c_double),
@@ -57,7 +58,7 @@ PROTOTYPES = {
     "jx_profiles": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "jx_sz_project": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, _vp]),
     "jx_sz_maps": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, _vp, _vp]),
-    "jx_sz_profile": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "jx_sz_profile": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "jx_xray": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, _vp]),
     "jx_cash_from_profiles": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp]),
     "jx_radial_profiles": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_double,

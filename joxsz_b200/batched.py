@@ -154,14 +154,14 @@ class BatchedLikelihood:
         return {k: v.cpu().numpy() for k, v in bufs.items() if v is not None}
 
     def sz_profile(self, theta):
-        """K3+K5: dict(row, bright [W,H], model [W,Nd], chisq [W])."""
+        """K3+K5: dict(row, bright [W,H], model [W,Nd], chisq [W], cint [W])."""
         t = self._theta_dev(theta); self._check_theta(t)
         W, p = t.shape[0], self.packed
         o = dict(row=self._new(W, p.H), bright=self._new(W, p.H), model=self._new(W, p.flux.size),
-                 chisq=self._new(W))
+                 chisq=self._new(W), cint=self._new(W))
         with torch.cuda.device(self.device):
             rc = self.lib.jx_sz_profile(self._h, _ptr(t), W, _ptr(o["row"]), _ptr(o["bright"]), _ptr(o["model"]),
-                                        _ptr(o["chisq"]), self._stream())
+                                        _ptr(o["chisq"]), _ptr(o["cint"]), self._stream())
         _lib.check(rc, self._h)
         return {k: v.cpu().numpy() for k, v in o.items()}
 

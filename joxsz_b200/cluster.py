@@ -200,7 +200,9 @@ def build_fit(inp: ClusterInputs, tables="synthetic", savedir="./"):
             ctr.ctcache[key] = (np.asarray(t0, dtype=np.float64), np.asarray(t1, dtype=np.float64))
 
     from . import funcs
-    mb.Fit.get_sz_like = MethodType(funcs.get_sz_like, fit)
-    mb.Fit.getLikelihood = MethodType(funcs.getLikelihood, fit)
-    mb.Fit.mylikeFromProfs = MethodType(funcs.mylikeFromProfs, fit)
+    # joxsz_main.py:186-188 binds these on the CLASS (so they always act on the last fit built); binding on
+    # the instance gives the same calls for a single fit and keeps several fits in one process independent
+    fit.get_sz_like = MethodType(funcs.get_sz_like, fit)
+    fit.getLikelihood = MethodType(funcs.getLikelihood, fit)
+    fit.mylikeFromProfs = MethodType(funcs.mylikeFromProfs, fit)
     return fit, sz_data

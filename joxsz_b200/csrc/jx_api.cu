@@ -90,7 +90,7 @@ void flush_stage_events(jx_handle* h) {
 }  // namespace
 
 extern "C" const char* jx_build_info(void) {
-    return "libjoxsz_b200 abi=" "3" " arch=sm_100a fp64 K1=profiles K2=dmma-project K3=fft256-szmap K4=xray K5=tail";
+    return "libjoxsz_b200 abi=" "4" " arch=sm_100a fp64 K1=profiles K2=dmma-project K3=fft256-szmap K4=xray K5=tail";
 }
 
 extern "C" const char* jx_last_error(const jx_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -143,6 +143,8 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
                               s->cts, s->srcscale, s->bkgterm};
     for (const void* p : required)
         if (!p) return bad("a required jx_setup array is NULL");
+    if (s->calc_integ && (!s->w_integ || !(s->integ_sig > 0.0) || !std::isfinite(s->integ_mu)))
+        return bad("calc_integ needs w_integ, a finite integ_mu and integ_sig > 0");
     if (!std::isfinite(s->prior_const)) return bad("prior_const is not finite (a frozen parameter is outside its prior)");
     for (int i = 0; i < s->nh * s->nh; ++i)
         if (s->seg[i] < 0 || s->seg[i] >= s->nseg) return bad("seg entry outside 0..nseg-1");
@@ -173,6 +175,7 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     d.hp8 = (s->nh + 7) & ~7; d.hp16 = (s->nh + 15) & ~15;
     d.nconv = s->nconv; d.nd = s->nd; d.na = s->na; d.nb = s->nb; d.ntab = s->ntab;
     d.tmin = s->tmin; d.tmax = s->tmax; d.max_walkers = s->max_walkers;
+    d.calc_integ = s->calc_integ ? 1 : 0; d.integ_mu = s->integ_mu; d.integ_sig = s->integ_sig;
 
     int rc = JX_OK;
 #define UP(field, src, count) if (!rc) rc = upload(h, &d.field, src, (size_t)(count))
@@ -233,6 +236,11 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
         std::vector<double> t((size_t)d.hp8 * d.hp8, 0.0);
         for (int u = 0; u < H; ++u) memcpy(&t[(size_t)u * d.hp8], s->hf + (size_t)u * H, sizeof(double) * H);
         rc = upload(h, &d.hf_pad, t.data(), t.size());
+    }
+    if (!rc) {
+        std::vector<double> t(s->nr, 0.0);
+        if (s->w_integ) memcpy(t.data(), s->w_integ, sizeof(double) * s->nr);
+        rc = upload(h, &d.w_integ, t.data(), t.size());
     }
     if (!rc) {
         std::vector<double> t(s->nr);
@@ -307,6 +315,7 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     if (!rc) rc = dev_alloc(h, &d.ws_ne, Wm * d.na);
     if (!rc) rc = dev_alloc(h, &d.ws_tx, Wm * d.na);
     if (!rc) rc = dev_alloc(h, &d.ws_prior, Wm);
+    if (!rc) rc = dev_alloc(h, &d.ws_integ, Wm);
     if (!rc) rc = dev_alloc(h, &d.ws_xlike, Wm);
     if (!rc) rc = dev_alloc(h, &d.ws_flags, Wm);
     if (!rc) rc = dev_alloc(h, &d.ws_coef, Wm * d.ncoef);
@@ -349,7 +358,8 @@ extern "C" int jx_loglike(jx_handle* h, const double* theta, int32_t W, double* 
         flush_stage_events(h);
         JX_CUDA(h, cudaEventRecord(h->ev[0], st));
     }
-    JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, d.ws_tsz, d.ws_ne, d.ws_tx, d.ws_flags, d.ws_prior, st));
+    JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, d.ws_tsz, d.ws_ne, d.ws_tx, d.ws_flags, d.ws_prior,
+                                  d.ws_integ, st));
     if (prof) JX_CUDA(h, cudaEventRecord(h->ev[1], st));
     JX_CUDA(h, jx_launch_xray(d, theta, d.ws_ne, d.ws_tx, W, nullptr, d.ws_xlike, d.ws_flags, st));
     if (prof) JX_CUDA(h, cudaEventRecord(h->ev[2], st));
@@ -358,8 +368,8 @@ extern "C" int jx_loglike(jx_handle* h, const double* theta, int32_t W, double* 
     JX_CUDA(h, jx_launch_szmap(d, d.ws_coef, d.ws_flags, W, h->sm_count, nullptr, d.ws_g, st));
     if (prof) JX_CUDA(h, cudaEventRecord(h->ev[4], st));
     JX_CUDA(h, jx_launch_gemm_nt(d.ws_g, d.hp8, d.dinv_t, d.hp8, d.ws_row, d.nh, W, d.nh, d.hp8, st));
-    JX_CUDA(h, jx_launch_tail(d, theta, d.ws_row, d.ws_tsz, d.ws_flags, d.ws_prior, d.ws_xlike, W, nullptr, nullptr,
-                              nullptr, ll, st));
+    JX_CUDA(h, jx_launch_tail(d, theta, d.ws_row, d.ws_tsz, d.ws_flags, d.ws_prior, d.ws_xlike, d.ws_integ, W, nullptr,
+                              nullptr, nullptr, ll, st));
     if (prof) {
         JX_CUDA(h, cudaEventRecord(h->ev[5], st));
         h->pending = true;
@@ -377,7 +387,7 @@ extern "C" int jx_profiles(jx_handle* h, const double* theta, int32_t W, double*
     cudaStream_t st = (cudaStream_t)stream;
     jx_dev& d = h->d;
     // X-ray positivity is part of the status bits: run K1 into the workspace copies K4 needs
-    JX_CUDA(h, jx_launch_profiles(d, theta, W, pp, d.nr, tsz, d.ws_ne, d.ws_tx, d.ws_flags, prior, st));
+    JX_CUDA(h, jx_launch_profiles(d, theta, W, pp, d.nr, tsz, d.ws_ne, d.ws_tx, d.ws_flags, prior, nullptr, st));
     JX_CUDA(h, jx_launch_xray(d, theta, d.ws_ne, d.ws_tx, W, nullptr, nullptr, d.ws_flags, st));
     if (ne_ann) JX_CUDA(h, cudaMemcpyAsync(ne_ann, d.ws_ne, sizeof(double) * W * d.na, cudaMemcpyDeviceToDevice, st));
     if (tx_ann) JX_CUDA(h, cudaMemcpyAsync(tx_ann, d.ws_tx, sizeof(double) * W * d.na, cudaMemcpyDeviceToDevice, st));
@@ -390,7 +400,7 @@ extern "C" int jx_sz_project(jx_handle* h, const double* theta, int32_t W, doubl
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     jx_dev& d = h->d;
-    JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+    JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
     if (y) JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.y_op, d.nr, y, st));
     if (coef) JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op_tap, d.ncoef, coef, st));
     return JX_OK;
@@ -415,7 +425,8 @@ extern "C" int jx_sz_maps(jx_handle* h, const double* theta, int32_t W, double* 
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     jx_dev& d = h->d;
-    JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, d.ws_tsz, nullptr, nullptr, nullptr, nullptr, st));
+    JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, d.ws_tsz, nullptr, nullptr, nullptr, nullptr, d.ws_integ,
+                                  st));
     JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op, d.ncoef, d.ws_coef, st));
     if (y2d) JX_CUDA(h, jx_launch_tap_y2d(d, d.ws_coef, W, y2d, st));
     if (conv2d || mapout) {
@@ -439,17 +450,19 @@ extern "C" int jx_sz_maps(jx_handle* h, const double* theta, int32_t W, double* 
 }
 
 extern "C" int jx_sz_profile(jx_handle* h, const double* theta, int32_t W, double* row, double* bright,
-                             double* model, double* chisq, void* stream) {
+                             double* model, double* chisq, double* cint, void* stream) {
     int rc = check_ready(h, theta, W);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     jx_dev& d = h->d;
-    JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, d.ws_tsz, nullptr, nullptr, nullptr, nullptr, st));
+    JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, d.ws_tsz, nullptr, nullptr, nullptr, nullptr, d.ws_integ,
+                                  st));
     JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op, d.ncoef, d.ws_coef, st));
     JX_CUDA(h, jx_launch_szmap(d, d.ws_coef, nullptr, W, h->sm_count, nullptr, d.ws_g, st));
     JX_CUDA(h, jx_launch_gemm_nt(d.ws_g, d.hp8, d.dinv_t, d.hp8, d.ws_row, d.nh, W, d.nh, d.hp8, st));
-    JX_CUDA(h, jx_launch_tail(d, theta, d.ws_row, d.ws_tsz, nullptr, nullptr, nullptr, W, bright, model, chisq, nullptr,
-                              st));
+    JX_CUDA(h, jx_launch_tail(d, theta, d.ws_row, d.ws_tsz, nullptr, nullptr, nullptr, nullptr, W, bright, model, chisq,
+                              nullptr, st));
+    if (cint) JX_CUDA(h, cudaMemcpyAsync(cint, d.ws_integ, sizeof(double) * W, cudaMemcpyDeviceToDevice, st));
     if (row) JX_CUDA(h, cudaMemcpyAsync(row, d.ws_row, sizeof(double) * W * d.nh, cudaMemcpyDeviceToDevice, st));
     return JX_OK;
 }
@@ -459,7 +472,7 @@ extern "C" int jx_xray(jx_handle* h, const double* theta, int32_t W, double* pre
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     jx_dev& d = h->d;
-    JX_CUDA(h, jx_launch_profiles(d, theta, W, nullptr, d.nr, nullptr, d.ws_ne, d.ws_tx, nullptr, nullptr, st));
+    JX_CUDA(h, jx_launch_profiles(d, theta, W, nullptr, d.nr, nullptr, d.ws_ne, d.ws_tx, nullptr, nullptr, nullptr, st));
     JX_CUDA(h, jx_launch_xray(d, theta, d.ws_ne, d.ws_tx, W, pred, cash, nullptr, st));
     return JX_OK;
 }

@@ -64,6 +64,9 @@ struct jx_dev {
     const double *conv_T, *conv_I;
     int nd;
     const double *g_op, *flux, *flux_err;
+    int calc_integ;
+    const double* w_integ;   // [nr] (zeros when the operator was not supplied)
+    double integ_mu, integ_sig;
     const double* g_op_t;    // [nh, nd] g_op transposed (K5 reads it coalesced over the data points)
     const double* dinv_t;    // [nh(v), hp8(kx)] dinv transposed, zero padded: row = G . dinv as an NT GEMM
     // X-ray
@@ -77,6 +80,7 @@ struct jx_dev {
     double* ws_ne;      // [W, na]
     double* ws_tx;      // [W, na]
     double* ws_prior;   // [W]
+    double* ws_integ;   // [W] integrated Compton parameter (K1)
     double* ws_xlike;   // [W]
     uint32_t* ws_flags; // [W]
     double* ws_coef;    // [W, ncoef]
@@ -107,7 +111,8 @@ struct jx_handle {
 
 // ---- launchers implemented by the kernel files (all asynchronous on `st`)
 cudaError_t jx_launch_profiles(const jx_dev& d, const double* theta, int W, double* pp, int ld_pp, double* tsz,
-                               double* ne_ann, double* tx_ann, uint32_t* flags, double* prior, cudaStream_t st);
+                               double* ne_ann, double* tx_ann, uint32_t* flags, double* prior, double* cint,
+                               cudaStream_t st);
 cudaError_t jx_launch_project(const jx_dev& d, const double* pp, int W, const double* op, int nout,
                               double* out, cudaStream_t st);
 cudaError_t jx_launch_xray(const jx_dev& d, const double* theta, const double* ne_ann, const double* tx_ann,
@@ -121,8 +126,8 @@ cudaError_t jx_launch_szmap(const jx_dev& d, const double* coef, const uint32_t*
                             double* convq, double* g, cudaStream_t st);
 // tail: row -> bright, model, chisq, ll (any output may be NULL)
 cudaError_t jx_launch_tail(const jx_dev& d, const double* theta, const double* row, const double* tsz,
-                           const uint32_t* flags, const double* prior, const double* xlike, int W, double* bright,
-                           double* model, double* chisq, double* ll, cudaStream_t st);
+                           const uint32_t* flags, const double* prior, const double* xlike, const double* cint, int W,
+                           double* bright, double* model, double* chisq, double* ll, cudaStream_t st);
 cudaError_t jx_szmap_configure(const jx_dev& d);   // one-time cudaFuncSetAttribute
 cudaError_t jx_launch_tap_y2d(const jx_dev& d, const double* coef, int W, double* y2d, cudaStream_t st);
 cudaError_t jx_launch_tap_expand(const jx_dev& d, const double* convq, int W, double* conv2d, cudaStream_t st);

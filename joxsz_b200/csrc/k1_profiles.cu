@@ -17,7 +17,7 @@ struct k1_args {
     jx_dev d;
     const double* theta;
     int W, ld_pp;
-    double *pp, *tsz, *ne_ann, *tx_ann, *prior;
+    double *pp, *tsz, *ne_ann, *tx_ann, *prior, *cint;
     uint32_t* flags;
 };
 
@@ -57,10 +57,12 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_profiles_kernel(const __grid
     if (wp.rc > wp.rs) flags |= JX_FLAG_RCRS;
 
     // ---- radial grid: pressure, T_SZ, mass
+    double ci = 0.0;        // integrated Compton parameter: a fixed linear functional of the pressure profile
     for (int i = lane; i < d.nr; i += 32) {
         const double r = __ldg(d.r_pp + i), lr = __ldg(d.ln_r_pp + i);
         double p, dp;
         jx_pressure(wp, r, lr, p, dp);
+        ci += __ldg(d.w_integ + i) * p;
         const double ne = jx_density(wp, lr);
         if (a.pp) a.pp[(size_t)w * a.ld_pp + i] = p;
         if (a.tsz && i < d.nt) a.tsz[(size_t)w * d.nt + i] = p / ne;
@@ -90,9 +92,11 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_profiles_kernel(const __grid
         if (a.ne_ann) a.ne_ann[(size_t)w * d.na + i] = ne;
         if (a.tx_ann) a.tx_ann[(size_t)w * d.na + i] = tsz * wp.tratio;
     }
+    ci = warp_sum(ci);
     if (lane == 0) {
         if (a.flags) a.flags[w] = flags;
         if (a.prior) a.prior[w] = prior_sum;
+        if (a.cint) a.cint[w] = ci;
     }
 }
 
@@ -131,9 +135,10 @@ __global__ void __launch_bounds__(256) k_radial_kernel(const __grid_constant__ k
 }  // namespace
 
 cudaError_t jx_launch_profiles(const jx_dev& d, const double* theta, int W, double* pp, int ld_pp, double* tsz,
-                               double* ne_ann, double* tx_ann, uint32_t* flags, double* prior, cudaStream_t st) {
+                               double* ne_ann, double* tx_ann, uint32_t* flags, double* prior, double* cint,
+                               cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
-    k1_args a{d, theta, W, ld_pp, pp, tsz, ne_ann, tx_ann, prior, flags};
+    k1_args a{d, theta, W, ld_pp, pp, tsz, ne_ann, tx_ann, prior, cint, flags};
     size_t smem = (size_t)K1_WARPS * (d.nr + JX_NPAR + 1) * sizeof(double);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {

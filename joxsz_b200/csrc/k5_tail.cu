@@ -6,6 +6,7 @@
 //   bright = map_out[N//2, N//2:] * convert([T0, T_SZ]) * calibration            (:472-473)
 //   model  = cubic spline through (radius[sep:], bright) at the data radii       (:476, fixed operator g_op)
 //   chisq  = nansum(((flux - model) / err)^2);  ll = (xray + prior) - chisq / 2  (:478-479, :536-538)
+//   with calc_integ: ll -= nansum(((cint - mu) / sig)^2) / 2, cint from K1       (:480-485)
 //
 // `row` = map_out[N//2, N//2:] comes from the map kernel's G vector through one small GEMM (jx_api.cu).
 // Walkers whose status bits are set get ll = -inf (the reference returns before / regardless of this
@@ -18,7 +19,7 @@ constexpr int K5_WARPS = 8;
 
 struct k5_args {
     jx_dev d;
-    const double *theta, *row, *tsz, *prior, *xlike;
+    const double *theta, *row, *tsz, *prior, *xlike, *cint;
     const uint32_t* flags;
     int W;
     double *bright, *model, *chisq, *ll;
@@ -86,7 +87,13 @@ __global__ void __launch_bounds__(K5_WARPS * 32) k5_tail_kernel(const __grid_con
         if (a.ll) {
             const double xl = a.xlike ? a.xlike[w] : 0.0;
             const double pr = a.prior ? a.prior[w] : 0.0;
-            a.ll[w] = (xl + pr) + (-c / 2.0);
+            double sz_ll = -c / 2.0;
+            if (d.calc_integ && a.cint) {       // joxsz_funcs.py:484-485; nansum drops a NaN term
+                double z = (a.cint[w] - d.integ_mu) / d.integ_sig;
+                z = z * z;
+                if (z == z) sz_ll -= z / 2.0;
+            }
+            a.ll[w] = (xl + pr) + sz_ll;
         }
     }
 }
@@ -94,10 +101,10 @@ __global__ void __launch_bounds__(K5_WARPS * 32) k5_tail_kernel(const __grid_con
 }  // namespace
 
 cudaError_t jx_launch_tail(const jx_dev& d, const double* theta, const double* row, const double* tsz,
-                           const uint32_t* flags, const double* prior, const double* xlike, int W, double* bright,
-                           double* model, double* chisq, double* ll, cudaStream_t st) {
+                           const uint32_t* flags, const double* prior, const double* xlike, const double* cint, int W,
+                           double* bright, double* model, double* chisq, double* ll, cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
-    k5_args a{d, theta, row, tsz, prior, xlike, flags, W, bright, model, chisq, ll};
+    k5_args a{d, theta, row, tsz, prior, xlike, cint, flags, W, bright, model, chisq, ll};
     const size_t smem = (size_t)K5_WARPS * d.nh * sizeof(double);
     k5_tail_kernel<<<(W + K5_WARPS - 1) / K5_WARPS, K5_WARPS * 32, smem, st>>>(a);
     return cudaGetLastError();

@@ -19,7 +19,9 @@ from .mb import mb
 # ----------------------------------------------------------------------------------------------
 
 def _signature(fit):
-    sig = [tuple(fit.thawed), bool(getattr(fit, "exclude_unphy_mass", False))]
+    sz = fit.data.sz
+    sig = [tuple(fit.thawed), bool(getattr(fit, "exclude_unphy_mass", False)),
+           (bool(getattr(sz, "calc_integ", False)), getattr(sz, "integ_mu", None), getattr(sz, "integ_sig", None))]
     for name, par in fit.pars.items():
         if name in fit.thawed:
             if hasattr(par, "prior_mu"):
@@ -65,23 +67,33 @@ def _squeeze(a, W_is_one):
 def get_sz_like(self, output="ll"):
     """SZ log-likelihood (or an intermediate) for the current parameters; reference ``joxsz_funcs.py:439-493``.
 
-    output: 'll' | 'chisq' | 'pp' (pressure profile on r_pp) | 'bright' (surface-brightness profile).
-    'integ' needs ``calc_integ=True``, which the GPU path does not implement.
+    output: 'll' | 'chisq' | 'pp' (pressure profile on r_pp) | 'bright' (surface-brightness profile) |
+    'integ' (integrated Compton parameter; only with ``calc_integ=True``, like the reference).
     """
     theta, W = _current_theta(self)
     eng = engine_for(self, W)
     one = W == 1
     if output == "pp":
         return _squeeze(eng.profiles(theta)["pp"], one)
-    if output in ("bright", "ll", "chisq"):
+    if output in ("bright", "ll", "chisq", "integ"):
         res = eng.sz_profile(theta)
         if output == "bright":
             return _squeeze(res["bright"], one)
         chisq = res["chisq"]
-        val = -chisq / 2 if output == "ll" else chisq
+        calc_integ = bool(getattr(self.data.sz, "calc_integ", False))
+        if output == "integ":
+            if not calc_integ:      # the reference falls through to its RuntimeError when calc_integ is off
+                raise RuntimeError('Unrecognised output name (must be "ll", "chisq", "pp", "bright" or "integ")')
+            val = res["cint"]
+        elif output == "ll":
+            val = -chisq / 2
+            if calc_integ:
+                with np.errstate(invalid="ignore"):
+                    pen = ((res["cint"] - self.data.sz.integ_mu) / self.data.sz.integ_sig) ** 2
+                val = val - np.where(np.isnan(pen), 0.0, pen) / 2
+        else:
+            val = chisq
         return float(val[0]) if one else val
-    if output == "integ":
-        raise NotImplementedError("calc_integ / 'integ' output is not implemented on the GPU path")
     raise RuntimeError('Unrecognised output name (must be "ll", "chisq", "pp", "bright" or "integ")')
 
 

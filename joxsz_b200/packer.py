@@ -57,6 +57,23 @@ def _convert_table(convert):
     return x, y
 
 
+def integ_weights(r_pp, kpc_as, step):
+    """``w`` with ``cint = w @ y`` for the reference's integrated Compton parameter
+    ``simps(concatenate((f(0), y)) * x, x) * 2 pi`` (``joxsz_funcs.py:481-483``), ``x`` in arcmin.
+
+    The Simpson weights are taken from the scipy that is installed (``simps`` where it still exists, else
+    ``simpson``) by integrating unit vectors, so the even-sample-count rule -- which changed in scipy 1.11 --
+    is whatever the user's reference run would apply.  ``x[0] = 0`` removes the ``f(0)`` term."""
+    import scipy.integrate as si
+    rule = getattr(si, "simps", None) or si.simpson
+    r_pp = np.asarray(r_pp, dtype=np.float64)
+    x = np.arange(0., r_pp[-1] / kpc_as / 60 + step / 60, step / 60)
+    if x.size != r_pp.size + 1:
+        raise PackError(f"integration grid has {x.size} samples for {r_pp.size} radii (joxsz_funcs.py:482 would raise)")
+    sw = np.asarray(rule(np.eye(x.size), x=x, axis=-1), dtype=np.float64)      # Simpson weight of each sample
+    return 2 * np.pi * sw[1:] * x[1:]
+
+
 class PackedSetup:
     """Numpy tables + the ``jx_setup`` struct that points into them (keep this object alive while
     the struct is in use)."""
@@ -72,9 +89,6 @@ class PackedSetup:
         self.ndim = len(thawed)
         if self.ndim < 1:
             raise PackError("no thawed parameters")
-        if getattr(sz, "calc_integ", False):
-            raise PackError("calc_integ=True (joxsz_funcs.py:480-487) is not implemented on the GPU path; "
-                            "its Simpson rule is scipy-version dependent (SURVEY.md 8a row S8)")
 
         # ---------------- parameters
         dens_mode = getattr(model.ne_cmpt, "mode", "single")
@@ -155,6 +169,13 @@ class PackedSetup:
         self.flux_r, self.flux, self.flux_err = (np.ascontiguousarray(flux[i]) for i in range(3))
         self.g_op = _f64(ops.spline_eval_operator(radius[sep:], self.flux_r))     # [Nd, H]
         self.N, self.H, self.sep, self.nr = N, H, sep, nr
+        # optional integrated-Compton-parameter penalty (joxsz_funcs.py:480-487)
+        self.calc_integ = bool(getattr(sz, "calc_integ", False))
+        self.w_integ = _f64(self.y_op.T @ integ_weights(r_pp, float(sz.kpc_as), float(sz.step)))
+        self.integ_mu = float(sz.integ_mu) if getattr(sz, "integ_mu", None) is not None else 0.0
+        self.integ_sig = float(sz.integ_sig) if getattr(sz, "integ_sig", None) is not None else 1.0
+        if self.calc_integ and not (self.integ_sig > 0 and math.isfinite(self.integ_mu)):
+            raise PackError("calc_integ=True needs a finite integ_mu and integ_sig > 0")
 
         # ---------------- X-ray tables
         na = int(annuli.nshells)
@@ -233,6 +254,8 @@ class PackedSetup:
         s.cmat, s.hf, s.dinv, s.filt_q = pd(self.cmat), pd(self.hf), pd(self.dinv), pd(self.filt_q)
         s.w_t0, s.conv_T, s.conv_I = pd(self.w_t0), pd(self.conv_T), pd(self.conv_I)
         s.g_op, s.flux, s.flux_err = pd(self.g_op), pd(self.flux), pd(self.flux_err)
+        s.calc_integ, s.w_integ = int(self.calc_integ), pd(self.w_integ)
+        s.integ_mu, s.integ_sig = self.integ_mu, self.integ_sig
         s.midpt_kpc, s.projvols, s.tlog = pd(self.midpt_kpc), pd(self.projvols), pd(self.tlog)
         s.lnrate0, s.lnrate1 = pd(self.lnrate0), pd(self.lnrate1)
         s.cts, s.srcscale, s.bkgterm = pd(self.cts), pd(self.srcscale), pd(self.bkgterm)

@@ -34,3 +34,15 @@ def cl1226_fit():
 def cl1226_oracle(cl1226_fit):
     from helpers import oracle_setup_from_fit
     return oracle_setup_from_fit(cl1226_fit)
+
+
+@pytest.fixture(scope="session")
+def cl1226_fit_integ():
+    """Same cluster with the integrated-Compton-parameter penalty on (reference ``calc_integ = True``)."""
+    from joxsz_b200 import cluster
+    from joxsz_b200.mb import mb
+    mb.fit.debugfit = False
+    inp = cluster.load_inputs_npz(os.path.join(ROOT, "tests", "golden", "cl1226_inputs.npz"))
+    inp.calc_integ = True
+    fit, sz = cluster.build_fit(inp, savedir=None)
+    return fit

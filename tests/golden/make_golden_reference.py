@@ -136,13 +136,24 @@ def main():
             out["xlike"][w] = fit.mylikeFromProfs(profs) if np.array(profs).min() > 0 else -np.inf
             out["mass"][w] = fit.mass_cmpt.mass_fun(fit.pars, sz.r_pp)
             out["tsz"][w] = fit.model.T_cmpt.temp_fun(fit.pars, sz.r_pp[:sz.sep], getT_SZ=True)
+    # second pass with the integrated-Compton-parameter penalty switched on (joxsz_funcs.py:480-487;
+    # `simps` is scipy's `simpson` of the installed version, see refstubs.py)
+    sz.calc_integ = True
+    out.update(ll_integ=np.empty(W), szll_integ=np.empty(W), cint=np.empty(W))
+    with np.errstate(all="ignore"):
+        for w in range(W):
+            out["ll_integ"][w] = fit.getLikelihood(thetas[w])
+            out["szll_integ"][w] = fit.get_sz_like(output="ll")
+            out["cint"][w] = fit.get_sz_like(output="integ")
+    sz.calc_integ = False
     print("finite ll:", int(np.isfinite(out["ll"]).sum()), "of", W, " ll[0] =", out["ll"][0])
     np.savez_compressed(
         os.path.join(HERE, "cl1226_golden.npz"), thawed=np.array(thawed), thetas=thetas,
         r_pp=sz.r_pp, radius=sz.radius, sep=np.array(sz.sep), kpc_as=np.array(sz.kpc_as),
         beam_2d=sz.beam_2d, filtering=sz.filtering, d_mat_row=sz.d_mat[sz.sep],
         midpt_kpc=fit.data.annuli.midpt_kpc, projvols_cm3=fit.data.annuli.projvols_cm3,
-        par_names=np.array(list(fit.pars.keys())), **out)
+        par_names=np.array(list(fit.pars.keys())), integ_mu=np.array(sz.integ_mu), integ_sig=np.array(sz.integ_sig),
+        scipy_version=np.array(__import__('scipy').__version__), **out)
 
 
 if __name__ == "__main__":

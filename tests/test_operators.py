@@ -83,5 +83,6 @@ def test_unsupported_geometry_is_rejected(cl1226_fit):
         PackedSetup(bad)
     bad.data.sz = copy.copy(sz)
     bad.data.sz.calc_integ = True
+    bad.data.sz.integ_sig = 0.0
     with pytest.raises(PackError):
         PackedSetup(bad)
