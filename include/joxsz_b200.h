@@ -181,9 +181,10 @@ int jx_cash_from_profiles(jx_handle* h, const double* pred, int32_t W, double* c
 
 /* Component methods at arbitrary radii (press_fun :275, press_derivative :289, vikhFunction :375,
  * temp_fun :321, mass_fun :428).  No handle: `pars` [W, JX_NPAR] holds full parameter vectors.
- * Outputs [W, n] each, NULL to skip. */
+ * `r` is one grid [n] shared by all walkers, or [W, n] when r_per_walker != 0 (the r_500 root search of
+ * joxsz_plots.py:316-339 evaluates each sample at its own radius).  Outputs [W, n] each, NULL to skip. */
 int jx_radial_profiles(const double* pars, int32_t W, int32_t dens_mode, const double* r, int32_t n,
-                       double mu_gas, double* press, double* dpress, double* ne, double* tsz, double* tx,
+                       int32_t r_per_walker, double mu_gas, double* press, double* dpress, double* ne, double* tsz, double* tx,
                        double* mass, int32_t device, void* stream);
 
 /* ---- ensemble stretch move (emcee RedBlueMove/StretchMove semantics; joxsz_main.py:206-210).

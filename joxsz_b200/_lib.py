@@ -61,7 +61,7 @@ PROTOTYPES = {
     "jx_sz_profile": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "jx_xray": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, _vp]),
     "jx_cash_from_profiles": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp]),
-    "jx_radial_profiles": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_double,
+    "jx_radial_profiles": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_double,
                                      _vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, _vp]),
     "jx_stretch_propose": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,
                                      C.c_uint64, C.c_uint64, _vp, _vp, C.c_int32, _vp]),

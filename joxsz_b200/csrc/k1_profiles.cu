@@ -105,6 +105,7 @@ struct kr_args {
     const double* pars;
     int W, dens_mode, n;
     const double* r;
+    int r_per_walker;
     double mu_gas;
     double *press, *dpress, *ne, *tsz, *tx, *mass;
 };
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(256) k_radial_kernel(const __grid_constant__ k
     __syncthreads();
     const jx_walker_pars wp = wp_s;
     for (int i = threadIdx.x; i < a.n; i += blockDim.x) {
-        const double r = a.r[i], lr = log(r);
+        const double r = a.r[(a.r_per_walker ? (size_t)w * a.n : 0) + i], lr = log(r);
         size_t o = (size_t)w * a.n + i;
         double p, dp;
         jx_pressure(wp, r, lr, p, dp);
@@ -152,11 +153,11 @@ cudaError_t jx_launch_profiles(const jx_dev& d, const double* theta, int W, doub
 }
 
 extern "C" int jx_radial_profiles(const double* pars, int32_t W, int32_t dens_mode, const double* r, int32_t n,
-                                  double mu_gas, double* press, double* dpress, double* ne, double* tsz,
+                                  int32_t r_per_walker, double mu_gas, double* press, double* dpress, double* ne, double* tsz,
                                   double* tx, double* mass, int32_t device, void* stream) {
     if (!pars || !r || W <= 0 || n <= 0) return JX_ERR_INVALID;
     if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
-    kr_args a{pars, W, dens_mode, n, r, mu_gas, press, dpress, ne, tsz, tx, mass};
+    kr_args a{pars, W, dens_mode, n, r, r_per_walker, mu_gas, press, dpress, ne, tsz, tx, mass};
     k_radial_kernel<<<W, 256, 0, (cudaStream_t)stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? JX_OK : JX_ERR_CUDA;
 }

@@ -22,7 +22,7 @@ _NEUTRAL = {"P_0": 1.0, "a": 1.0, "b": 1.0, "c": 0.0, "r_p": 1.0, "log(n_0)": 0.
             "Z": 0.0, "backscale": 1.0, "calibration": 1.0}
 
 
-def evaluate(pars, r_kpc, kind, need, mode="single", mu_gas=0.61, device=None):
+def evaluate(pars, r_kpc, kind, need, mode="single", mu_gas=0.61, device=None, per_walker_r=False):
     if not torch.cuda.is_available():
         raise _lib.JxError("profile evaluation runs on the GPU only (no CPU implementation in this package)")
     lib = _lib.load()
@@ -42,16 +42,24 @@ def evaluate(pars, r_kpc, kind, need, mode="single", mu_gas=0.61, device=None):
     for i, name in enumerate(_lib.PARAM_SLOTS):
         full[:, i] = vals[name] if name in vals else _NEUTRAL[name]
     r = np.asarray(r_kpc, dtype=np.float64)
-    rf = np.ascontiguousarray(r.reshape(-1))
+    if per_walker_r:        # r_kpc is [W, n]: walker w is evaluated on its own row
+        if r.ndim != 2 or r.shape[0] != W:
+            raise ValueError(f"per-walker radii must be [W={W}, n], got {r.shape}")
+        n = r.shape[1]
+        rf = np.ascontiguousarray(r.reshape(-1))
+        r = r[0]
+    else:
+        rf = np.ascontiguousarray(r.reshape(-1))
+        n = rf.size
     d_pars = torch.from_numpy(full).to(dev)
     d_r = torch.from_numpy(rf).to(dev)
-    out = torch.empty((W, rf.size), dtype=torch.float64, device=dev)
+    out = torch.empty((W, n), dtype=torch.float64, device=dev)
     args = [C.c_void_p(None)] * 6
     args[_KIND_ARG[kind]] = C.c_void_p(out.data_ptr())
     with torch.cuda.device(dev):
         rc = lib.jx_radial_profiles(C.c_void_p(d_pars.data_ptr()), W, 1 if mode == "double" else 0,
-                                    C.c_void_p(d_r.data_ptr()), rf.size, float(mu_gas), *args, dev.index,
-                                    C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+                                    C.c_void_p(d_r.data_ptr()), n, int(bool(per_walker_r)), float(mu_gas), *args,
+                                    dev.index, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
     _lib.check(rc, None)
     res = out.cpu().numpy()
     if not batched:
