@@ -205,4 +205,7 @@ def build_fit(inp: ClusterInputs, tables="synthetic", savedir="./"):
     fit.get_sz_like = MethodType(funcs.get_sz_like, fit)
     fit.getLikelihood = MethodType(funcs.getLikelihood, fit)
     fit.mylikeFromProfs = MethodType(funcs.mylikeFromProfs, fit)
+    fit.calcProfiles = MethodType(funcs.calcProfiles, fit)
+    from . import fitting
+    fit.doFitting = MethodType(fitting.doFitting, fit)      # batched multi-start simplex instead of the serial scipy loop
     return fit, sz_data

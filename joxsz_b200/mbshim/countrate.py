@@ -40,8 +40,9 @@ class CountRate:
         return self.ctcache[key]
 
     def getCountRate(self, rmf, arf, minenergy_keV, maxenergy_keV, NH_1022, T_keV, Z_solar, ne_cm3):
-        t0, t1 = self.getTables(rmf, arf, minenergy_keV, maxenergy_keV, NH_1022)
-        logT = np.log(np.clip(T_keV, self.Tmin, self.Tmax))
-        r0 = np.exp(np.interp(logT, self.Tlogvals, t0))
-        r1 = np.exp(np.interp(logT, self.Tlogvals, t1))
-        return (r0 + (r1 - r0) * Z_solar) * ne_cm3 ** 2
+        """mbproj2 evaluates ``(exp(interp0) + (exp(interp1) - exp(interp0)) Z) ne^2`` here on the host.  In this
+        package that arithmetic exists only in the CUDA kernel K4 (``jx_xray``): use ``fit.calcProfiles()`` /
+        ``BatchedLikelihood.xray``.  (The golden-vector generator patches a numpy restatement in for the run
+        of the reference's own code: tests/golden/refstubs.py.)"""
+        raise NotImplementedError("CountRate.getCountRate has no host implementation here: the count rates are "
+                                  "computed on the GPU (jx_xray); call fit.calcProfiles()")

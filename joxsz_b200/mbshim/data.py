@@ -45,14 +45,10 @@ class Band:
         self.areascales = np.ones_like(self.cts) if areascales is None else np.asarray(areascales, dtype=np.float64)
 
     def calcProjProfile(self, annuli, ne_prof, T_prof, Z_prof, NH_1022pcm2, backscale=1.0):
-        rates = annuli.ctrate.getCountRate(self.rmf, self.arf, self.emin_keV, self.emax_keV,
-                                           NH_1022pcm2, T_prof, Z_prof, ne_prof)
-        projrates = annuli.projvols_cm3.dot(rates)
-        projrates = projrates * (self.areascales * self.exposures)
-        if self.backrates is not None:
-            projrates = projrates + (self.backrates * backscale * annuli.geomarea_arcmin2
-                                     * self.areascales * self.exposures)
-        return projrates
+        """mbproj2 projects the shell count rates through ``projvols_cm3`` here on the host.  In this package the
+        projection exists only in the CUDA kernel K4 (``jx_xray``): use ``fit.calcProfiles()``."""
+        raise NotImplementedError("Band.calcProjProfile has no host implementation here: predicted profiles are "
+                                  "computed on the GPU (jx_xray); call fit.calcProfiles()")
 
 
 class Data:

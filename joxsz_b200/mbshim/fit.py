@@ -23,10 +23,9 @@ class Fit:
             self.pars[name].val = val
 
     def calcProfiles(self):
-        ne_prof, T_prof, Z_prof = self.model.computeProfs(self.pars)
-        return [band.calcProjProfile(self.data.annuli, ne_prof, T_prof, Z_prof,
-                                     self.model.NH_1022pcm2, backscale=self.pars["backscale"].val)
-                for band in self.data.bands]
+        """Predicted X-ray profiles per band for the current parameters, computed on the GPU (K1 + K4)."""
+        from ..funcs import calcProfiles
+        return calcProfiles(self)
 
     def getLikelihood(self, vals=None):
         raise NotImplementedError("bind joxsz_funcs.getLikelihood (joxsz_main.py:187)")

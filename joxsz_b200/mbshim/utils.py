@@ -36,11 +36,9 @@ def projectionVolumeMatrix(radii):
 
 
 def cashLogLikelihood(data, model):
-    """Cash statistic as a log-likelihood, ``sum(data*log(model)) - sum(model)``; -inf if not finite."""
-    like = np.sum(data * np.log(model)) - np.sum(model)
-    if np.isfinite(like):
-        return like
-    return -np.inf
+    """mbproj2's Cash log-likelihood ``sum(data*log(model)) - sum(model)``.  Evaluated on the GPU in this
+    package (``jx_cash_from_profiles`` behind ``fit.mylikeFromProfs``); no host implementation."""
+    raise NotImplementedError("cashLogLikelihood has no host implementation here: use fit.mylikeFromProfs(profs)")
 
 
 class AtomicWriteFile:

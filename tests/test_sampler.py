@@ -221,3 +221,41 @@ def test_device_sampler_on_the_cluster_likelihood(cl1226_fit, cl1226_oracle):
         s2.step()
     assert np.array_equal(s2.coords_host(), coords)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_mcmc_run_schedule_end_to_end(cl1226_fit, cl1226_oracle, tmp_path):
+    """The reference's driver sequence (joxsz_main.py:196-214): sampler on fit.getLikelihood, mcmc_run with its
+    pre-fit / burn-in / sampling schedule, then the chain in emcee's layouts and the saved attributes."""
+    from helpers import orc
+    from joxsz_b200 import add_backend_attrs
+    from joxsz_b200.sampler import mcmc_run
+    from joxsz_b200.synthetic import FIDUCIAL
+    fit = cl1226_fit
+    saved = fit.thawedParVals()
+    try:
+        fit.updateThawed([FIDUCIAL[n] for n in fit.thawed])
+        nwalkers, nburn, nlength, nthin = 30, 40, 60, 5            # joxsz_main.py:42-45 uses 30 / 2000 / 5000 / 5
+        np.random.seed(7)
+        mcmc = EnsembleSampler(nwalkers, len(fit.thawed), fit.getLikelihood, pool=None, backend=None, seed=7)
+        mcmc.initspread = .1
+        assert mcmc_run(mcmc, fit, nburn, nlength, nthin, max_prefit=1)
+        cube_chain = mcmc.chain                                     # (nwalkers x niter x nparams)
+        assert cube_chain.shape == (nwalkers, nlength // nthin, len(fit.thawed))
+        flat_chain = cube_chain.reshape(-1, cube_chain.shape[2], order='F')
+        assert np.isfinite(flat_chain).all()
+        lp = mcmc.get_log_prob()
+        assert lp.shape == (nlength // nthin, nwalkers) and np.isfinite(lp).all()
+        # stored log-probs are the likelihood of the stored positions
+        last = mcmc.get_chain()[-1]
+        ref = orc.BatchedOracle(cl1226_oracle).loglike(last)
+        assert np.max(np.abs(ref - lp[-1])) < 1e-6
+        assert 0.02 < np.mean(mcmc.acceptance_fraction) < 0.9
+        path = str(tmp_path / "chain.npz")
+        mcmc.save_npz(path)
+        add_backend_attrs(path, fit, nburn, nthin)
+        z = np.load(path)
+        assert z["chain"].shape == (nlength // nthin, nwalkers, len(fit.thawed))
+        assert [k.decode() for k in z["param_names"]] == list(fit.thawed) and int(z["burn"]) == nburn
+    finally:
+        fit.updateThawed(saved)
