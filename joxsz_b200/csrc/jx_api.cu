@@ -90,7 +90,7 @@ void flush_stage_events(jx_handle* h) {
 }  // namespace
 
 extern "C" const char* jx_build_info(void) {
-    return "libjoxsz_b200 abi=" "4" " arch=sm_100a fp64 K1=profiles K2=dmma-project K3=fft256-szmap K4=xray K5=tail";
+    return "libjoxsz_b200 abi=" "4" " arch=sm_100a fp64 K1=profiles K2=dmma-project K3=fft256-szmap(smem)|fft512/1024-szmap(L2) K4=xray K5=tail";
 }
 
 extern "C" const char* jx_last_error(const jx_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -130,7 +130,8 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     if (s->nh != s->nmap / 2 + 1) return bad("nh must equal nmap/2 + 1");
     if (s->nt != s->nh - 1) return bad("nt (sep) must equal nh - 1 (joxsz_funcs.py:469-473)");
     if (s->nt > s->nr) return bad("sep exceeds len(r_pp)");
-    if (s->npad != 256) return bad("only cyclic length P = 256 is implemented by the map kernel");
+    if (s->npad != 256 && s->npad != 512 && s->npad != 1024)
+        return bad("cyclic length P must be 256 (shared-memory map kernel), 512 or 1024 (L2-staged map kernel)");
     if (s->nh > s->npad / 2 + 1) return bad("map quarter plane does not fit the cyclic length");
     if (s->nseg < 1 || s->nseg > 65535) return bad("nseg out of range");
     if (s->na < 1 || s->na > 32) return bad("1..32 annuli supported (one lane per annulus)");
@@ -173,6 +174,7 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     d.nr = s->nr; d.nrp = (s->nr + 7) & ~7; d.nt = s->nt; d.nmap = s->nmap; d.nh = s->nh; d.npad = s->npad;
     d.nq = s->npad / 2 + 1; d.nseg = s->nseg; d.ncoef = 4 * s->nseg;
     d.hp8 = (s->nh + 7) & ~7; d.hp16 = (s->nh + 15) & ~15;
+    d.xs_pitch = ((d.nq > d.hp16 ? d.nq : d.hp16) + 1) & ~1;
     d.nconv = s->nconv; d.nd = s->nd; d.na = s->na; d.nb = s->nb; d.ntab = s->ntab;
     d.tmin = s->tmin; d.tmax = s->tmax; d.max_walkers = s->max_walkers;
     d.calc_integ = s->calc_integ ? 1 : 0; d.integ_mu = s->integ_mu; d.integ_sig = s->integ_sig;
@@ -321,13 +323,22 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     if (!rc) rc = dev_alloc(h, &d.ws_coef, Wm * d.ncoef);
     if (!rc) rc = dev_alloc(h, &d.ws_row, Wm * d.nh);
     if (!rc) rc = dev_alloc(h, &d.ws_g, Wm * d.hp8);
-    if (!rc) {
+    if (!rc && d.npad == 256) {
         size_t smem = jx_szmap_smem_bytes(d);
         if (smem > (size_t)prop.sharedMemPerBlockOptin) {
             rc = fail(h, JX_ERR_INVALID, "map kernel needs more shared memory than the device offers");
         } else {
             cudaError_t e = jx_szmap_configure(d);
             if (e != cudaSuccess) rc = cuda_fail(h, e, "configure map kernel");
+        }
+    }
+    if (!rc && d.npad != 256) {
+        if (!jx_szmap_large_supported(d) || jx_szmap_large_smem_bytes(d) > (size_t)prop.sharedMemPerBlockOptin) {
+            rc = fail(h, JX_ERR_INVALID, "large-map kernel: geometry does not fit the shared memory of an SM");
+        } else {
+            cudaError_t e = jx_szmap_large_configure(d);
+            if (e != cudaSuccess) rc = cuda_fail(h, e, "configure large-map kernel");
+            if (!rc) rc = dev_alloc(h, &d.ws_scratch, (size_t)h->sm_count * d.hp8 * d.xs_pitch);
         }
     }
     if (rc) {
@@ -337,6 +348,14 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     }
     *out = h;
     return JX_OK;
+}
+
+// map stage: shared-memory kernel when the cyclic length is 256, L2-staged kernel otherwise
+static cudaError_t launch_map(jx_handle* h, const double* coef, const uint32_t* flags, int W, double* convq,
+                              double* g, cudaStream_t st) {
+    const jx_dev& d = h->d;
+    if (d.npad == 256) return jx_launch_szmap(d, coef, flags, W, h->sm_count, convq, g, st);
+    return jx_launch_szmap_large(d, coef, flags, W, h->sm_count, convq, g, d.ws_scratch, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -365,7 +384,7 @@ extern "C" int jx_loglike(jx_handle* h, const double* theta, int32_t W, double* 
     if (prof) JX_CUDA(h, cudaEventRecord(h->ev[2], st));
     JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op, d.ncoef, d.ws_coef, st));
     if (prof) JX_CUDA(h, cudaEventRecord(h->ev[3], st));
-    JX_CUDA(h, jx_launch_szmap(d, d.ws_coef, d.ws_flags, W, h->sm_count, nullptr, d.ws_g, st));
+    JX_CUDA(h, launch_map(h, d.ws_coef, d.ws_flags, W, nullptr, d.ws_g, st));
     if (prof) JX_CUDA(h, cudaEventRecord(h->ev[4], st));
     JX_CUDA(h, jx_launch_gemm_nt(d.ws_g, d.hp8, d.dinv_t, d.hp8, d.ws_row, d.nh, W, d.nh, d.hp8, st));
     JX_CUDA(h, jx_launch_tail(d, theta, d.ws_row, d.ws_tsz, d.ws_flags, d.ws_prior, d.ws_xlike, d.ws_integ, W, nullptr,
@@ -431,7 +450,7 @@ extern "C" int jx_sz_maps(jx_handle* h, const double* theta, int32_t W, double* 
     if (y2d) JX_CUDA(h, jx_launch_tap_y2d(d, d.ws_coef, W, y2d, st));
     if (conv2d || mapout) {
         if ((rc = ensure_convq(h, W))) return rc;
-        JX_CUDA(h, jx_launch_szmap(d, d.ws_coef, nullptr, W, h->sm_count, d.ws_convq, d.ws_g, st));
+        JX_CUDA(h, launch_map(h, d.ws_coef, nullptr, W, d.ws_convq, d.ws_g, st));
         if (conv2d) JX_CUDA(h, jx_launch_tap_expand(d, d.ws_convq, W, conv2d, st));
         if (mapout) {
             if (h->tap_scratch_walkers < (size_t)W) {
@@ -458,7 +477,7 @@ extern "C" int jx_sz_profile(jx_handle* h, const double* theta, int32_t W, doubl
     JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, d.ws_tsz, nullptr, nullptr, nullptr, nullptr, d.ws_integ,
                                   st));
     JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op, d.ncoef, d.ws_coef, st));
-    JX_CUDA(h, jx_launch_szmap(d, d.ws_coef, nullptr, W, h->sm_count, nullptr, d.ws_g, st));
+    JX_CUDA(h, launch_map(h, d.ws_coef, nullptr, W, nullptr, d.ws_g, st));
     JX_CUDA(h, jx_launch_gemm_nt(d.ws_g, d.hp8, d.dinv_t, d.hp8, d.ws_row, d.nh, W, d.nh, d.hp8, st));
     JX_CUDA(h, jx_launch_tail(d, theta, d.ws_row, d.ws_tsz, nullptr, nullptr, nullptr, nullptr, W, bright, model, chisq,
                               nullptr, st));

@@ -52,6 +52,8 @@ struct jx_dev {
     const double* filt_q;    // [nh, nh]
     // derived at jx_create
     int hp8, hp16;           // nh rounded up to 8 / 16
+    int xs_pitch;            // large-map path: doubles per row of the per-CTA scratch map (even, >= nq and hp16)
+    double* ws_scratch;      // large-map path: [sm_count][hp8][xs_pitch]
     const uint16_t* seg16;   // [nh, nh] seg narrowed
     const double* costab;    // [nmap] cos(2 pi m / nmap)
     const double* hf_pad;    // [hp8, hp8] hf zero padded
@@ -134,6 +136,12 @@ cudaError_t jx_launch_tap_expand(const jx_dev& d, const double* convq, int W, do
 cudaError_t jx_launch_tap_mapout(const jx_dev& d, const double* convq, int W, double* mapout, double* scratch,
                                  cudaStream_t st);
 size_t jx_szmap_smem_bytes(const jx_dev& d);
+// large-map path (cyclic length 512 / 1024, working set in an L2-resident global scratch): k3l_szmap.cu
+bool jx_szmap_large_supported(const jx_dev& d);
+size_t jx_szmap_large_smem_bytes(const jx_dev& d);
+cudaError_t jx_szmap_large_configure(const jx_dev& d);
+cudaError_t jx_launch_szmap_large(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
+                                  double* convq, double* g, double* scratch, cudaStream_t st);
 
 // ---- small device helpers
 JX_D double warp_sum(double v) {

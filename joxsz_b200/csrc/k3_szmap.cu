@@ -23,7 +23,7 @@
 // cosine transform), reduced over ky analytically because only the central row is consumed.
 // The per-walker inputs (spline coefficients) arrive by TMA bulk copy (cp.async.bulk + mbarrier),
 // double buffered against the previous walker's compute.
-#include "jx_fft.cuh"
+#include "k3_common.cuh"
 
 namespace {
 
@@ -32,14 +32,6 @@ constexpr int K3_THREADS_MIN = 256;      // fallback when the larger exchange bu
 constexpr int K3_P = 256;
 constexpr int K3_Q = K3_P / 2 + 1;       // 129
 constexpr int K3_XS = 130;               // row pitch of xs (doubles): XS/2 odd -> conflict-free column walks
-
-struct k3_args {
-    jx_dev d;
-    const double* coef;
-    const uint32_t* flags;
-    int W;
-    double *convq, *g;
-};
 
 struct k3_smem_layout {
     size_t tw, xbuf, xs, coef, gpart, mbar, total;
@@ -53,106 +45,10 @@ __host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8, in
     L.xbuf = take((size_t)(nthreads / 16) * JX_XB_ELEMS * sizeof(double2));
     L.xs = take((size_t)hp8 * K3_XS * sizeof(double));
     L.coef = take((size_t)2 * d.ncoef * sizeof(double));
-    L.gpart = take((size_t)2 * hp8 * sizeof(double));
+    L.gpart = take((size_t)JX_D_MAXSPLIT * hp8 * sizeof(double));
     L.mbar = take(2 * sizeof(uint64_t));
     L.total = o;
     return L;
-}
-
-JX_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-JX_D void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
-}
-JX_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-JX_D void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-JX_D void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "JX_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra JX_DONE;\n"
-        "bra JX_WAIT;\n"
-        "JX_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-JX_D void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-// value of the Compton-y spline on piece `s` at offset `t` from its left knot; the 4 coefficients of a
-// piece are adjacent (two 16-byte shared loads), Horner evaluation
-JX_D double spline_eval(const double* __restrict__ c, int s, double t) {
-    const double2 c01 = *reinterpret_cast<const double2*>(c + 4 * s);
-    const double2 c23 = *reinterpret_cast<const double2*>(c + 4 * s + 2);
-    return c01.x + t * (c01.y + t * (c23.x + t * c23.y));
-}
-
-// Phase D of the map kernel: G[kx] = sum_u hf[u, kx] sum_v conv_c[u, v] w_v cos(2 pi kx v / N) on the FP64
-// tensor cores.  Work item = (kx tile, part of the u tiles); NSPLIT = 1 when there are at least as many
-// warps as kx tiles (one item holds every u tile: the cosine fragments are loaded once), else 2.  Every
-// item runs exactly NUT u-tiles so the DMMA loop carries no predicates: with NSPLIT = 2 and an odd tile
-// count the second part starts one tile early and leaves that tile out of the final fold.  The cosine
-// fragments come from L2 (d.cfrag, fragment order) through a 4-deep register prefetch queue.
-template <int NUT>
-JX_D void k3_phase_d(const jx_dev& d, const double* __restrict__ xs, double* __restrict__ gpart_s, int warp, int lane,
-                     int nwarps, int nsplit) {
-    const int hp8 = d.hp8, ntile = hp8 >> 3, nks = d.hp16 >> 2;      // nks is a multiple of 4
-    const int frow = lane >> 2, fk = lane & 3;
-    const int voff = (fk & 1) + 8 * (fk >> 1);          // k-permutation {0,1,8,9}: conflict-free fragments
-    for (int item = warp; item < nsplit * ntile; item += nwarps) {
-        const int jt = item % ntile, part = item / ntile;
-        const int ut_lo = part ? ntile - NUT : 0;
-        double acc[NUT][2];
-#pragma unroll
-        for (int i = 0; i < NUT; ++i) acc[i][0] = acc[i][1] = 0.0;
-        const double* arow = xs + (size_t)(ut_lo * 8 + frow) * K3_XS + voff;
-        const double* bp = d.cfrag + (size_t)jt * nks * 32 + lane;     // B fragments, one coalesced load per k step
-        double bq[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) bq[q] = __ldg(bp + q * 32);
-        for (int ks0 = 0; ks0 < nks; ks0 += 4) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const double b = bq[q];
-                if (ks0 + 4 < nks) bq[q] = __ldg(bp + (ks0 + 4 + q) * 32);
-                const double* ap = arow + 4 * ks0 + 2 * q;             // 16 (ks >> 2) + 2 (ks & 3), ks = ks0 + q
-                double af[NUT];
-#pragma unroll
-                for (int i = 0; i < NUT; ++i) af[i] = ap[(size_t)i * 8 * K3_XS];
-#pragma unroll
-                for (int i = 0; i < NUT; ++i) dmma884(acc[i][0], acc[i][1], af[i], b);
-            }
-        }
-        // fold in hf[u, kx] and reduce over the 8 fragment rows
-        double g0 = 0.0, g1 = 0.0;
-        const int kc = jt * 8 + 2 * fk;
-#pragma unroll
-        for (int i = 0; i < NUT; ++i) {
-            if (part && ut_lo + i < NUT) continue;      // tile already covered by the first part (warp-uniform)
-            const double2 h = __ldg(reinterpret_cast<const double2*>(
-                d.hf_pad + (size_t)((ut_lo + i) * 8 + frow) * hp8 + kc));
-            g0 += acc[i][0] * h.x;
-            g1 += acc[i][1] * h.y;
-        }
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-            g0 += __shfl_xor_sync(0xffffffffu, g0, o);
-            g1 += __shfl_xor_sync(0xffffffffu, g1, o);
-        }
-        if (lane < 4) {
-            gpart_s[part * hp8 + kc] = g0;
-            gpart_s[part * hp8 + kc + 1] = g1;
-        }
-    }
 }
 
 template <int NT>
@@ -338,18 +234,14 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
 
         // ================= phase D: G[kx] = sum_u hf[u,kx] sum_v conv_c[u,v] w_v cos(2 pi kx v/N)   (DMMA)
         {
-            const int ntile = hp8 >> 3, nwarps = NT / 32;
-            const int nsplit = ntile <= nwarps ? 1 : 2;
-            switch ((ntile + nsplit - 1) / nsplit) {
-#define JX_D_CASE(n) case n: k3_phase_d<n>(d, xs, gpart_s, warp, lane, nwarps, nsplit); break;
-                JX_D_CASE(1) JX_D_CASE(2) JX_D_CASE(3) JX_D_CASE(4) JX_D_CASE(5) JX_D_CASE(6)
-                JX_D_CASE(7) JX_D_CASE(8) JX_D_CASE(9) JX_D_CASE(10) JX_D_CASE(11)
-                default: k3_phase_d<12>(d, xs, gpart_s, warp, lane, nwarps, nsplit); break;
-#undef JX_D_CASE
-            }
+            const int nsplit = k3_run_phase_d<K3_XS>(d, xs, K3_XS, gpart_s, warp, lane, NT / 32);
             __syncthreads();
             // G[kx] leaves the kernel; row = G . dinv and the tail are batched over walkers afterwards
-            if (tid < hp8) a.g[(size_t)w * hp8 + tid] = nsplit == 1 ? gpart_s[tid] : gpart_s[tid] + gpart_s[hp8 + tid];
+            if (tid < hp8) {
+                double g = gpart_s[tid];
+                for (int p = 1; p < nsplit; ++p) g += gpart_s[p * hp8 + tid];
+                a.g[(size_t)w * hp8 + tid] = g;
+            }
         }
         // the next iteration's first barrier orders these reads of gpart_s / xs before they are rewritten
     }
@@ -451,7 +343,7 @@ cudaError_t jx_launch_szmap(const jx_dev& d, const double* coef, const uint32_t*
                             double* convq, double* g, cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
     k3_args a;
-    a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.g = g;
+    a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.g = g; a.scratch = nullptr;
     const int nt = k3_pick_threads(d);
     k3_smem_layout L = k3_layout(d, d.hp8, nt);
     int grid = W < sm_count ? W : sm_count;

@@ -182,7 +182,7 @@ def quarter(a):
     return np.ascontiguousarray(a[c:, c:])
 
 
-SUPPORTED_FFT_SIZES = (256,)
+SUPPORTED_FFT_SIZES = (256, 512, 1024)     # 256: shared-memory map kernel; 512 / 1024: L2-staged map kernel
 
 
 def choose_padded_size(n_map, n_beam, supported=SUPPORTED_FFT_SIZES):
