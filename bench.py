@@ -40,22 +40,43 @@ TOTAL_WALKERS = 65536
 # shared set-up
 # ----------------------------------------------------------------------------------------------
 
+WORKLOAD = "cl1226"          # set from --workload before anything is built (also in the CPU pool workers)
+
+WORKLOADS = {
+    # name: (map_half, nr) of joxsz_b200.cluster.synthetic_inputs; None = the shipped cluster
+    "cl1226": None,
+    "synth255": (127, 512),      # BASELINE config 3: 512-point grid, 255-pixel map (nearest odd side to 256)
+    "synth511": (255, 1024),     # BASELINE config 5: 1024-point grid, 511-pixel map (nearest odd side to 512)
+}
+
+
 def build_cluster():
     from joxsz_b200 import cluster
     from joxsz_b200.mb import mb
     mb.fit.debugfit = False
     inp = cluster.load_inputs_npz(os.path.join(ROOT, "tests", "golden", "cl1226_inputs.npz"))
+    if WORKLOADS[WORKLOAD] is not None:
+        map_half, nr = WORKLOADS[WORKLOAD]
+        inp = cluster.synthetic_inputs(map_half=map_half, nr=nr, base=inp)
     fit, _ = cluster.build_fit(inp, savedir=None)
     return fit
 
 
 def workload_config(extra=None):
-    cfg = {"workload": "CL J1226.9+3332 (shipped example) scaled to 65,536 walkers: Nr=313, map 171x171, "
-                       "beam 55x55, 19 SZ points, 10 bands x 15 annuli, 13 free parameters; "
-                       "step = one stretch-move ensemble iteration (65,536 likelihood evaluations)",
-           "walkers": TOTAL_WALKERS, "nr": 313, "map": 171, "ndim": 13,
-           "xray_tables": "synthetic (XSPEC unavailable)",
-           "l2_policy": "inputs and intermediates per step (> 400 MB) exceed the 126 MB L2; no flush needed"}
+    if WORKLOAD == "cl1226":
+        cfg = {"workload": "CL J1226.9+3332 (shipped example) scaled to 65,536 walkers: Nr=313, map 171x171, "
+                           "beam 55x55, 19 SZ points, 10 bands x 15 annuli, 13 free parameters; "
+                           "step = one stretch-move ensemble iteration (65,536 likelihood evaluations)",
+               "walkers": TOTAL_WALKERS, "nr": 313, "map": 171, "ndim": 13}
+    else:
+        map_half, nr = WORKLOADS[WORKLOAD]
+        n = 2 * map_half + 1
+        cfg = {"workload": f"synthetic cluster (joxsz_b200.cluster.synthetic_inputs): Nr={nr}, map {n}x{n} (the reference "
+                           f"builds odd sides only), Gaussian beam 55x55, normal-cdf transfer function, shipped X-ray "
+                           f"layout; step = one stretch-move ensemble iteration",
+               "walkers": TOTAL_WALKERS, "nr": nr, "map": n, "ndim": 13}
+    cfg.update({"xray_tables": "synthetic (XSPEC unavailable)",
+                "l2_policy": "inputs and intermediates per step (> 400 MB) exceed the 126 MB L2; no flush needed"})
     if extra:
         cfg.update(extra)
     return cfg
@@ -125,8 +146,9 @@ class ClockSampler:
 _ORACLE_SETUP = None
 
 
-def _cpu_init():
-    global _ORACLE_SETUP
+def _cpu_init(workload="cl1226"):
+    global _ORACLE_SETUP, WORKLOAD
+    WORKLOAD = workload
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     from helpers import oracle_setup_from_fit
@@ -150,7 +172,7 @@ def make_pool():
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     ctx = mp.get_context("fork")
-    pool = ctx.Pool(cores, initializer=_cpu_init)
+    pool = ctx.Pool(cores, initializer=_cpu_init, initargs=(WORKLOAD,))
     pool.map(_noop, range(cores * 2))
     return pool, cores
 
@@ -284,7 +306,7 @@ def run_gpu_arm(args):
         tfd = C.c_double(0.0)
         eng.lib.jx_measure_dmma_tflops(local, C.byref(tfd))
         flops = pk.algorithmic_flops()
-        roof = {"bound": "hbm", "kernel": "k3_szmap_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": "k3_szmap_kernel" if WORKLOAD == "cl1226" else "k3l_szmap_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_walker": alg["szmap"], "walkers_per_launch": k3_walkers,
                 "avg_launch_ms": k3_avg_s * 1e3, "launches_timed": int(k3_n),
@@ -296,6 +318,8 @@ def run_gpu_arm(args):
         stage_ms = {k: (v[0] / ncalls) for k, v in stages.items()}
         # DRAM traffic of the dominant kernel from the committed ncu capture of this same command (per launch)
         try:
+            if WORKLOAD != "cl1226":
+                raise KeyError("no ncu capture for this workload")
             tr = json.load(open(os.path.join(ROOT, "profiles", "k3_ncu_traffic.json")))
             roof["traffic"] = tr["dram_bytes_per_launch"] * (k3_walkers / tr["walkers_per_launch"])
             roof["traffic_source"] = tr.get("source")
@@ -354,7 +378,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--walkers", type=int, default=TOTAL_WALKERS)
+    ap.add_argument("--workload", default="cl1226", choices=sorted(WORKLOADS),
+                    help="cl1226 = the configuration the metric is quoted on (default); synth255 / synth511 = the "
+                         "larger synthetic clusters of BASELINE configs 3 and 5")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     if args.impl == "reference":
         run_reference_arm(args)
     else:
