@@ -297,13 +297,13 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
         d.bhat_sw = reinterpret_cast<const double2*>(dev);
     }
     if (!rc) {   // phase-D cosine matrix in mma.m8n8k4 B-fragment order: [kx tile][k step][lane]
-        const int ntile = d.hp8 / 8, nks = d.hp16 / 4;
+        const int ntile = d.hp8 / 8, nks = d.hp8 / 4;
         std::vector<double> t((size_t)ntile * nks * 32, 0.0);
         for (int jt = 0; jt < ntile; ++jt)
             for (int ks = 0; ks < nks; ++ks)
                 for (int lane = 0; lane < 32; ++lane) {
                     const int kx = jt * 8 + (lane >> 2), fk = lane & 3;
-                    const int v = 16 * (ks >> 2) + 2 * (ks & 3) + (fk & 1) + 8 * (fk >> 1);
+                    const int v = 8 * (ks >> 1) + 2 * (ks & 1) + (fk & 1) + 4 * (fk >> 1);
                     if (kx < H && v < H)
                         t[((size_t)jt * nks + ks) * 32 + lane] =
                             cos(2.0 * M_PI * (double)(((long long)kx * v) % s->nmap) / (double)s->nmap) * (v ? 2.0 : 1.0);

@@ -63,10 +63,12 @@ JX_D double spline_eval(const double* __restrict__ c, int s, double t) {
 template <int NUT, int PITCH>
 JX_D void k3_phase_d(const jx_dev& d, const double* __restrict__ xs, int pitch, double* __restrict__ gpart_s, int warp,
                      int lane, int nwarps, int nsplit) {
-    const int hp8 = d.hp8, ntile = hp8 >> 3, nks = d.hp16 >> 2;      // nks is a multiple of 4
+    const int hp8 = d.hp8, ntile = hp8 >> 3, nks = hp8 >> 2;          // K = hp8 in steps of 4: nks is even
     const int ld = PITCH ? PITCH : pitch;
     const int frow = lane >> 2, fk = lane & 3;
-    const int voff = (fk & 1) + 8 * (fk >> 1);          // k-permutation {0,1,8,9}: conflict-free fragments
+    // k-permutation: step ks covers v = 8 (ks >> 1) + 2 (ks & 1) + {0, 1, 4, 5}; with a row pitch = 2 (mod 16)
+    // doubles every 8-byte bank pair is hit by exactly two lanes: 2 wavefronts per 256-byte fragment load
+    const int voff = (fk & 1) + 4 * (fk >> 1);
     for (int item = warp; item < nsplit * ntile; item += nwarps) {
         const int jt = item % ntile, part = item / ntile;
         const int ut_first = part * NUT;                                  // first tile this part is responsible for
@@ -78,19 +80,26 @@ JX_D void k3_phase_d(const jx_dev& d, const double* __restrict__ xs, int pitch, 
         const double* bp = d.cfrag + (size_t)jt * nks * 32 + lane;     // B fragments, one coalesced load per k step
         double bq[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) bq[q] = __ldg(bp + q * 32);
-        for (int ks0 = 0; ks0 < nks; ks0 += 4) {
+        for (int q = 0; q < 4; ++q) bq[q] = q < nks ? __ldg(bp + q * 32) : 0.0;
+        auto kstep = [&](const double b, const double* ap) {
+            double af[NUT];
+#pragma unroll
+            for (int i = 0; i < NUT; ++i) af[i] = ap[(size_t)i * 8 * ld];
+#pragma unroll
+            for (int i = 0; i < NUT; ++i) dmma884(acc[i][0], acc[i][1], af[i], b);
+        };
+        int ks0 = 0;
+        for (; ks0 + 4 <= nks; ks0 += 4) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const double b = bq[q];
-                if (ks0 + 4 < nks) bq[q] = __ldg(bp + (ks0 + 4 + q) * 32);
-                const double* ap = arow + 4 * ks0 + 2 * q;             // 16 (ks >> 2) + 2 (ks & 3), ks = ks0 + q
-                double af[NUT];
-#pragma unroll
-                for (int i = 0; i < NUT; ++i) af[i] = ap[(size_t)i * 8 * ld];
-#pragma unroll
-                for (int i = 0; i < NUT; ++i) dmma884(acc[i][0], acc[i][1], af[i], b);
+                if (ks0 + 4 + q < nks) bq[q] = __ldg(bp + (ks0 + 4 + q) * 32);
+                kstep(b, arow + 4 * ks0 + 8 * (q >> 1) + 2 * (q & 1));
             }
+        }
+        if (ks0 < nks) {                                                 // two steps left
+            kstep(bq[0], arow + 4 * ks0);
+            kstep(bq[1], arow + 4 * ks0 + 2);
         }
         // fold in hf[u, kx] and reduce over the 8 fragment rows
         double g0 = 0.0, g1 = 0.0;

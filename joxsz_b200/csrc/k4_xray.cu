@@ -26,19 +26,30 @@ struct k4_args {
     uint32_t* flags;
 };
 
-// numpy.interp for one abscissa on an increasing grid: clamps outside, NaN propagates
-JX_D double np_interp(double x, const double* __restrict__ xp, const double* __restrict__ fp, int n) {
-    if (x != x) return x;
-    if (x > __ldg(xp + n - 1)) return __ldg(fp + n - 1);
-    if (x < __ldg(xp)) return __ldg(fp);
-    if (x == __ldg(xp + n - 1)) return __ldg(fp + n - 1);
+// numpy.interp on an increasing grid, split in two so that the search runs once per shell and is shared by
+// the 2 x nb tables: `np_interp_locate` returns the segment index (or -1 / -2 / -3 for "clamp to the first
+// value" / "clamp to the last value" / NaN abscissa) and np_interp_eval applies numpy's formula
+// slope * (x - x0) + f0 on that segment.
+JX_D int np_interp_locate(double x, const double* __restrict__ xp, int n) {
+    if (x != x) return -3;
+    if (x > __ldg(xp + n - 1)) return -2;
+    if (x < __ldg(xp)) return -1;
+    if (x == __ldg(xp + n - 1)) return -2;
     int lo = 0, hi = n - 1;          // invariant: xp[lo] <= x < xp[hi]
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
         if (x >= __ldg(xp + mid)) lo = mid; else hi = mid;
     }
-    double x0 = __ldg(xp + lo), f0 = __ldg(fp + lo);
-    double slope = (__ldg(fp + lo + 1) - f0) / (__ldg(xp + lo + 1) - x0);
+    return lo;
+}
+
+JX_D double np_interp_eval(int lo, double x, double x0, const double* __restrict__ xp,
+                           const double* __restrict__ fp, int n) {
+    if (lo == -3) return x;
+    if (lo == -2) return __ldg(fp + n - 1);
+    if (lo == -1) return __ldg(fp);
+    const double f0 = __ldg(fp + lo);
+    const double slope = (__ldg(fp + lo + 1) - f0) / (__ldg(xp + lo + 1) - x0);
     return slope * (x - x0) + f0;
 }
 
@@ -66,10 +77,16 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_xray_kernel(const __grid_con
         double Tc = (T != T) ? T : fmin(fmax(T, d.tmin), d.tmax);
         lnT = log(Tc);
     }
+    int seg_t = -3;
+    double x0_t = 0.0;
+    if (s < d.na) {
+        seg_t = np_interp_locate(lnT, d.tlog, d.ntab);
+        if (seg_t >= 0) x0_t = __ldg(d.tlog + seg_t);
+    }
     for (int b = 0; b < d.nb; ++b) {
         if (s < d.na) {
-            double r0 = exp(np_interp(lnT, d.tlog, d.lnrate0 + (size_t)b * d.ntab, d.ntab));
-            double r1 = exp(np_interp(lnT, d.tlog, d.lnrate1 + (size_t)b * d.ntab, d.ntab));
+            double r0 = exp(np_interp_eval(seg_t, lnT, x0_t, d.tlog, d.lnrate0 + (size_t)b * d.ntab, d.ntab));
+            double r1 = exp(np_interp_eval(seg_t, lnT, x0_t, d.tlog, d.lnrate1 + (size_t)b * d.ntab, d.ntab));
             rate_s[s] = (r0 + (r1 - r0) * Z) * (ne * ne);
         }
         __syncwarp();
