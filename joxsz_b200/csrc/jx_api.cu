@@ -323,6 +323,11 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     if (!rc) rc = dev_alloc(h, &d.ws_coef, Wm * d.ncoef);
     if (!rc) rc = dev_alloc(h, &d.ws_row, Wm * d.nh);
     if (!rc) rc = dev_alloc(h, &d.ws_g, Wm * d.hp8);
+    if (!rc) {
+        cudaError_t e = jx_profiles_configure(d);
+        if (e == cudaSuccess) e = jx_gemm_configure();
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "configure profile / GEMM kernels");
+    }
     if (!rc && d.npad == 256) {
         size_t smem = jx_szmap_smem_bytes(d);
         if (smem > (size_t)prop.sharedMemPerBlockOptin) {

@@ -120,6 +120,8 @@ cudaError_t jx_launch_project(const jx_dev& d, const double* pp, int W, const do
 cudaError_t jx_launch_xray(const jx_dev& d, const double* theta, const double* ne_ann, const double* tx_ann,
                            int W, double* pred, double* cash, uint32_t* flags, cudaStream_t st);
 cudaError_t jx_launch_cash(const jx_dev& d, const double* pred, int W, double* cash, cudaStream_t st);
+cudaError_t jx_profiles_configure(const jx_dev& d);   // one-time per device (jx_create)
+cudaError_t jx_gemm_configure();
 cudaError_t jx_launch_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N,
                               int Kpad, cudaStream_t st);
 // production map stage: coef -> G[kx] (+ optional quarter-plane convolved map).  `flags` may be NULL

@@ -135,18 +135,19 @@ __global__ void __launch_bounds__(256) k_radial_kernel(const __grid_constant__ k
 
 }  // namespace
 
+// per device, at jx_create: opt in to more than 48 KB of dynamic shared memory when the radial grid needs it
+cudaError_t jx_profiles_configure(const jx_dev& d) {
+    const size_t smem = (size_t)K1_WARPS * (d.nr + JX_NPAR + 1) * sizeof(double);
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(k1_profiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
 cudaError_t jx_launch_profiles(const jx_dev& d, const double* theta, int W, double* pp, int ld_pp, double* tsz,
                                double* ne_ann, double* tx_ann, uint32_t* flags, double* prior, double* cint,
                                cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
     k1_args a{d, theta, W, ld_pp, pp, tsz, ne_ann, tx_ann, prior, cint, flags};
     size_t smem = (size_t)K1_WARPS * (d.nr + JX_NPAR + 1) * sizeof(double);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k1_profiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
     int blocks = (W + K1_WARPS - 1) / K1_WARPS;
     k1_profiles_kernel<<<blocks, K1_WARPS * 32, smem, st>>>(a);
     return cudaGetLastError();

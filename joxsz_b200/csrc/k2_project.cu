@@ -122,17 +122,15 @@ k2_dgemm_nt_kernel(const double* __restrict__ A, int lda, const double* __restri
 
 }  // namespace
 
+// per device, at jx_create
+cudaError_t jx_gemm_configure() {
+    return cudaFuncSetAttribute(k2_dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM);
+}
+
 // C[M, N] = A[M, Kpad] . B[N, Kpad]^T; lda/ldb even, A and B zero padded up to Kpad (a multiple of 8)
 cudaError_t jx_launch_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N,
                               int Kpad, cudaStream_t st) {
     if (M <= 0 || N <= 0) return cudaSuccess;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k2_dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)K2_SMEM);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     k2_dgemm_nt_kernel<<<grid, K2_THREADS, K2_SMEM, st>>>(A, lda, B, ldb, C, ldc, M, N, Kpad);
     return cudaGetLastError();
