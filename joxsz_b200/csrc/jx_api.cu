@@ -280,15 +280,17 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
         d.nsynth = (int)t.size();
         rc = upload(h, &d.synth, t.data(), t.size());
     }
-    if (!rc) {   // beam spectrum per column pair in the register order of the column FFT: [cp][p][t] = bhat[fold(t+16 rev16(p)), 2cp..2cp+1]
+    if (!rc) {   // beam spectrum per column pair in the register order of the nine-thread column FFT:
+                 // [cp][p][t] = bhat[fold(t + 16 rev16(p)), 2cp..2cp+1], t = 0..8
         const int ncp = (Q + 1) / 2, P = s->npad;
-        std::vector<double> t((size_t)ncp * 16 * 16 * 2, 0.0);
+        std::vector<double> t((size_t)ncp * 16 * 9 * 2, 0.0);
         for (int cp = 0; cp < ncp; ++cp)
             for (int p = 0; p < 16; ++p)
-                for (int th = 0; th < 16; ++th) {
+                for (int th = 0; th < 9; ++th) {
                     const int n = th + 16 * ((p >> 2) + 4 * (p & 3));
                     const int f = n <= P / 2 ? n : P - n;
-                    const size_t o = (((size_t)cp * 16 + p) * 16 + th) * 2;
+                    const size_t o = (((size_t)cp * 16 + p) * 9 + th) * 2;
+                    if (f >= Q) continue;               // cyclic lengths other than 256 use the large-map kernel
                     t[o] = s->bhat[(size_t)f * Q + 2 * cp];
                     t[o + 1] = 2 * cp + 1 < Q ? s->bhat[(size_t)f * Q + 2 * cp + 1] : 0.0;
                 }

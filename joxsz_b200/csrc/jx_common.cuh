@@ -59,7 +59,7 @@ struct jx_dev {
     const double* hf_pad;    // [hp8, hp8] hf zero padded
     const jx_synth_px* synth; // [nsynth] quarter-plane pixels with u <= v, padded with u = 0xffff sentinels
     int nsynth;               // multiple of 256
-    const double2* bhat_sw;  // [ceil(nq/2)][16][16] beam spectrum of column pair cp in FFT thread order (K3 phase B)
+    const double2* bhat_sw;  // [ceil(nq/2)][16][9] beam spectrum of column pair cp in FFT thread order (K3 phase B: position p, thread t = 0..8)
     const double* cfrag;     // [hp8/8][hp8/4][32] w_v cos(2 pi kx v / N) in DMMA B-fragment order (K3 phase D)
     const double* w_t0;      // [nt]
     int nconv;

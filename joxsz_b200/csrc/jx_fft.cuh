@@ -123,5 +123,39 @@ JX_HD void fft256_pass2(int q, double (&re)[16], double (&im)[16], const double2
     dft16(re, im);
 }
 
+// ---- even sequences: x[n] = x[256 - n] ---------------------------------------------------------------
+// Every transform of the cyclic-length-256 map kernel acts on an even complex sequence (two real even
+// sequences packed as real / imaginary part).  Pass 1 of thread 16 - t is then determined by thread t,
+//   A_{16-t}[k2] w256^((16-t) k2) = conj(w256^(t k2)) A_t[-k2],
+// and the spectrum is even as well, so a group of NINE threads (t = 0..8) does the whole transform: thread t
+// writes its own exchange column and the mirrored one, thread q = 0..8 of pass 2 ends with X[q + 16 k1],
+// k1 = 0..15, and those 9 x 16 values cover every index of the folded half-array (fold256).  Three groups
+// share a warp (27 of 32 lanes).  Only exchange rows k2 = 0..8 are ever read.
+constexpr int JX_XE_ROWS = 9;
+constexpr int JX_XE_ELEMS = JX_XE_ROWS * JX_XB_PITCH;     // double2 elements per 9-thread group
+
+JX_HD void fft256e_pass1(int t, double (&re)[16], double (&im)[16], const double2* __restrict__ tw,
+                         double2* __restrict__ xbuf) {
+    dft16(re, im);
+    const bool mirror = t >= 1 && t <= 7;
+#pragma unroll
+    for (int k2 = 0; k2 < JX_XE_ROWS; ++k2) {
+        const int pd = rev16(k2), pm = rev16((16 - k2) & 15);
+        double r = re[pd], i = im[pd], mr = re[pm], mi = im[pm];
+        if (k2 != 0) {
+            const double2 w = tw[k2 * 16 + t];
+            const double tr = r * w.x - i * w.y;
+            i = r * w.y + i * w.x;
+            r = tr;
+            const double tm = mr * w.x + mi * w.y;        // times conj(w)
+            mi = mi * w.x - mr * w.y;
+            mr = tm;
+        }
+        xbuf[k2 * JX_XB_PITCH + t] = make_double2(r, i);
+        if (mirror) xbuf[k2 * JX_XB_PITCH + 16 - t] = make_double2(mr, mi);
+    }
+}
+// pass 2 of thread q = 0..8 is fft256_pass2 (it reads exchange row q only)
+
 // index of the even extension: sequence value at n (0 <= n < 256) is the half-array value at fold256(n)
 JX_HD constexpr int fold256(int n) { return n <= 128 ? n : 256 - n; }

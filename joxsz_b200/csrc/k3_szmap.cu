@@ -24,17 +24,37 @@
 // The per-walker inputs (spline coefficients) arrive by TMA bulk copy (cp.async.bulk + mbarrier),
 // double buffered against the previous walker's compute.
 #include "k3_common.cuh"
+#include <stdlib.h>
+
+// Developer instrumentation (scripts/k3_phase_clocks.py builds a private copy of the library with
+// -DJX_K3_CLOCKS): SM cycles per phase, summed over CTAs and walkers.  Never compiled into the shipped library.
+#ifdef JX_K3_CLOCKS
+__device__ unsigned long long jx_k3_clk[8];
+#define K3_CLK_DECL long long k3_t0 = clock64()
+#define K3_CLK(i) do { if (threadIdx.x == 0) { long long k3_t1 = clock64(); atomicAdd(&jx_k3_clk[i], (unsigned long long)(k3_t1 - k3_t0)); k3_t0 = k3_t1; } } while (0)
+extern "C" int jx_debug_k3_clocks(unsigned long long* out8) {
+    cudaError_t e = cudaMemcpyFromSymbol(out8, jx_k3_clk, sizeof(jx_k3_clk));
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(jx_k3_clk, z, sizeof(z));
+    return e == cudaSuccess ? 0 : -1;
+}
+#else
+#define K3_CLK_DECL
+#define K3_CLK(i)
+#endif
 
 namespace {
 
-constexpr int K3_THREADS_MAX = 384;      // 24 FFT groups: 43 row pairs -> 2 rounds, 65 column pairs -> 3 rounds
-constexpr int K3_THREADS_MIN = 256;      // fallback when the larger exchange buffer does not fit
+// CTA sizes, largest first; the first whose exchange buffers fit next to the map in shared memory is used.
+// 512 threads = 16 warps x 3 nine-thread FFT groups (43 row pairs -> 1 round, 65 column pairs -> 2 rounds) at
+// 128 registers per thread.
+constexpr int K3_NT_A = 512, K3_NT_B = 384, K3_NT_C = 256;
 constexpr int K3_P = 256;
 constexpr int K3_Q = K3_P / 2 + 1;       // 129
 constexpr int K3_XS = 130;               // row pitch of xs (doubles): XS/2 odd -> conflict-free column walks
 
 struct k3_smem_layout {
-    size_t tw, xbuf, xs, coef, gpart, mbar, total;
+    size_t tw, xbuf, xs, coef, gpart, segjt, mbar, total;
 };
 
 __host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8, int nthreads) {
@@ -42,10 +62,14 @@ __host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8, in
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~size_t(15); return at; };
     L.tw = take(256 * sizeof(double2));
-    L.xbuf = take((size_t)(nthreads / 16) * JX_XB_ELEMS * sizeof(double2));
+    L.xbuf = take((size_t)(nthreads / 32) * 3 * JX_XE_ELEMS * sizeof(double2));
     L.xs = take((size_t)hp8 * K3_XS * sizeof(double));
     L.coef = take((size_t)2 * d.ncoef * sizeof(double));
-    L.gpart = take((size_t)JX_D_MAXSPLIT * hp8 * sizeof(double));
+    {
+        const size_t split = (size_t)JX_D_MAXSPLIT * hp8, flat = (size_t)(nthreads / 32) * JX_DF_MAXSEG * 8;
+        L.gpart = take((split > flat ? split : flat) * sizeof(double));
+    }
+    L.segjt = take((size_t)(nthreads / 32) * JX_DF_MAXSEG * sizeof(int));
     L.mbar = take(2 * sizeof(uint64_t));
     L.total = o;
     return L;
@@ -62,12 +86,20 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
     double* xs = reinterpret_cast<double*>(k3_raw + L.xs);
     double* coef_s = reinterpret_cast<double*>(k3_raw + L.coef);
     double* gpart_s = reinterpret_cast<double*>(k3_raw + L.gpart);
+    int* segjt_s = reinterpret_cast<int*>(k3_raw + L.segjt);
+    const bool dflat = false && k3_dflat_ok(hp8, NT / 32);   // measured slower than one kx tile per warp here
     uint64_t* mbar = reinterpret_cast<uint64_t*>(k3_raw + L.mbar);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int grp = tid >> 4, t = tid & 15;
-    const unsigned gmask = 0xffffu << (lane & 16);           // the 16 lanes of this FFT group
-    double2* xbuf = xbuf_all + (size_t)grp * JX_XB_ELEMS;
+    // FFT groups: every sequence the kernel transforms is even, so nine threads carry one length-256 transform
+    // (jx_fft.cuh) and a warp holds three groups; lanes 27..31 shadow the first lanes of group 2 (same loads,
+    // same exchange values) and never store results
+    constexpr int NW = NT / 32;
+    const bool lane_on = lane < 27;
+    const int fg = lane_on ? lane / 9 : 2;
+    const int t = lane_on ? lane - 9 * fg : lane - 27;
+    const bool t_edge = t == 0 || t == 8;                   // threads whose outputs beyond index 128 repeat earlier ones
+    double2* xbuf = xbuf_all + (size_t)(warp * 3 + fg) * JX_XE_ELEMS;
     const uint32_t coef_bytes = (uint32_t)(d.ncoef * sizeof(double));
 
     // ---- one-time set-up of the CTA
@@ -108,6 +140,7 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
         }
 
         double re[16], im[16];
+        K3_CLK_DECL;
 
         // ================= phase A0: synthesise the quarter-plane map into xs[u, v].  The map is radial, so
         // pixel (u, v) also fills (v, u); the table lists u <= v in thread order (one coalesced 16-byte load
@@ -134,11 +167,13 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
             }
         }
         __syncthreads();
+        K3_CLK(0);
 
         // ================= phase A1: transform the rows along x, in place
         const int npair = (H + 1) >> 1;
-        for (int rp = grp; rp < npair; rp += (NT / 16)) {
-            const int u0 = 2 * rp, u1 = u0 + 1;
+        for (int base = warp * 3; base < npair; base += 3 * NW) {
+            const bool ok = lane_on && base + fg < npair;
+            const int u0 = 2 * (base + fg < npair ? base + fg : npair - 1), u1 = u0 + 1;
             const bool has1 = u1 < H;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -150,24 +185,28 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
                 }
                 re[j] = vr; im[j] = vi;
             }
-            fft256_pass1(t, re, im, tw_s, xbuf);
-            __syncwarp(gmask);
+            fft256e_pass1(t, re, im, tw_s, xbuf);
+            __syncwarp();
             fft256_pass2(t, re, im, xbuf);
-            __syncwarp(gmask);
+            __syncwarp();
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
-                const int k = t + 16 * rev16(p);
-                if (k < K3_Q) {
+                const int n = t + 16 * rev16(p);                     // spectrum index held at position p
+                if (ok && !(n > 128 && t_edge)) {
+                    const int k = fold256(n);
                     xs[u0 * K3_XS + k] = re[p];
                     if (has1) xs[u1 * K3_XS + k] = im[p];
                 }
             }
         }
         __syncthreads();
+        K3_CLK(1);
 
         // ================= phase B: columns -- cyclic convolution with the beam along y
         const int ncpair = (K3_Q + 1) >> 1;
-        for (int cp = grp; cp < ncpair; cp += (NT / 16)) {
+        for (int base = warp * 3; base < ncpair; base += 3 * NW) {
+            const bool ok = lane_on && base + fg < ncpair;
+            const int cp = base + fg < ncpair ? base + fg : ncpair - 1;
             const int kx = 2 * cp;
             const bool has1 = kx + 1 < K3_Q;
 #pragma unroll
@@ -175,35 +214,39 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
                 const int f = fold256(t + 16 * j);
                 double2 v = make_double2(0.0, 0.0);
                 if (f < H) v = *reinterpret_cast<const double2*>(xs + f * K3_XS + kx);
-                re[j] = v.x; im[j] = v.y;
+                re[j] = v.x; im[j] = has1 ? v.y : 0.0;
             }
-            fft256_pass1(t, re, im, tw_s, xbuf);
-            __syncwarp(gmask);
+            fft256e_pass1(t, re, im, tw_s, xbuf);
+            __syncwarp();
             fft256_pass2(t, re, im, xbuf);
-            __syncwarp(gmask);
+            __syncwarp();
             double re2[16], im2[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {           // spectrum * beam, back to natural register order
-                // beam spectrum of this column pair in thread order [cp][p][t]: 256 contiguous bytes per group
-                const double2 bh = __ldg(d.bhat_sw + ((size_t)cp * 16 + rev16(j)) * 16 + t);
+                // beam spectrum of this column pair in thread order [cp][p][t]: 144 contiguous bytes per group
+                const double2 bh = __ldg(d.bhat_sw + ((size_t)cp * 16 + rev16(j)) * 9 + t);
                 re2[j] = re[rev16(j)] * bh.x;
                 im2[j] = im[rev16(j)] * bh.y;
             }
-            fft256_pass1(t, re2, im2, tw_s, xbuf);
-            __syncwarp(gmask);
+            fft256e_pass1(t, re2, im2, tw_s, xbuf);
+            __syncwarp();
             fft256_pass2(t, re2, im2, xbuf);
-            __syncwarp(gmask);
+            __syncwarp();
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
-                const int u = t + 16 * rev16(p);
-                if (u < H) *reinterpret_cast<double2*>(xs + u * K3_XS + kx) = make_double2(re2[p], im2[p]);
+                const int n = t + 16 * rev16(p);
+                const int u = fold256(n);
+                if (ok && u < H && !(n > 128 && t_edge))
+                    *reinterpret_cast<double2*>(xs + u * K3_XS + kx) = make_double2(re2[p], has1 ? im2[p] : 0.0);
             }
         }
         __syncthreads();
+        K3_CLK(2);
 
         // ================= phase C: rows back to pixel space, in place: xs[u, v] = conv_c[u, v]
-        for (int rp = grp; rp < npair; rp += (NT / 16)) {
-            const int u0 = 2 * rp, u1 = u0 + 1;
+        for (int base = warp * 3; base < npair; base += 3 * NW) {
+            const bool ok = lane_on && base + fg < npair;
+            const int u0 = 2 * (base + fg < npair ? base + fg : npair - 1), u1 = u0 + 1;
             const bool has1 = u1 < H;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -211,21 +254,27 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
                 re[j] = xs[u0 * K3_XS + f];
                 im[j] = has1 ? xs[u1 * K3_XS + f] : 0.0;
             }
-            fft256_pass1(t, re, im, tw_s, xbuf);
-            __syncwarp(gmask);
+            fft256e_pass1(t, re, im, tw_s, xbuf);
+            __syncwarp();
             fft256_pass2(t, re, im, xbuf);
-            __syncwarp(gmask);
+            // every lane of the warp has read its row pair: the in-place stores below cannot overtake them
+            __syncwarp();
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
-                const int v = t + 16 * rev16(p);
-                if (v < hp16) {
+                const int n = t + 16 * rev16(p);
+                const int v = fold256(n);
+                if (ok && v < hp16 && !(n > 128 && t_edge)) {
                     const bool in = v < H;
                     xs[u0 * K3_XS + v] = in ? re[p] : 0.0;
                     if (has1) xs[u1 * K3_XS + v] = in ? im[p] : 0.0;
                 }
             }
         }
+        // phase D's first cosine fragments come from L2: start them before waiting for the other warps
+        k3_dflat_state dst;
+        if (dflat) dst = k3_dflat_begin(d, warp, lane, NT / 32);
         __syncthreads();
+        K3_CLK(3);
 
         if (a.convq) {
             double* cq = a.convq + (size_t)w * H * H;
@@ -233,16 +282,27 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
         }
 
         // ================= phase D: G[kx] = sum_u hf[u,kx] sum_v conv_c[u,v] w_v cos(2 pi kx v/N)   (DMMA)
-        {
+        // G[kx] leaves the kernel; row = G . dinv and the tail are batched over walkers afterwards
+        if (dflat) {
+            k3_run_phase_d_flat(d, xs, K3_XS, dst, gpart_s, segjt_s, warp, lane);
+            __syncthreads();
+            if (tid < hp8) {
+                const int jt = tid >> 3, c = tid & 7;
+                double g = 0.0;
+                for (int sl = 0; sl < (NT / 32) * JX_DF_MAXSEG; ++sl)
+                    if (segjt_s[sl] == jt) g += gpart_s[sl * 8 + c];
+                a.g[(size_t)w * hp8 + tid] = g;
+            }
+        } else {
             const int nsplit = k3_run_phase_d<K3_XS>(d, xs, K3_XS, gpart_s, warp, lane, NT / 32);
             __syncthreads();
-            // G[kx] leaves the kernel; row = G . dinv and the tail are batched over walkers afterwards
             if (tid < hp8) {
                 double g = gpart_s[tid];
                 for (int p = 1; p < nsplit; ++p) g += gpart_s[p * hp8 + tid];
                 a.g[(size_t)w * hp8 + tid] = g;
             }
         }
+        K3_CLK(4);
         // the next iteration's first barrier orders these reads of gpart_s / xs before they are rewritten
     }
 }
@@ -322,19 +382,24 @@ __global__ void k3_tap_mapout_kernel(jx_dev d, const double* costab, const doubl
 
 }  // namespace
 
-// 384 threads when its exchange buffers fit the 227 KB of shared memory a CTA can have, else 256
 static int k3_pick_threads(const jx_dev& d) {
-    return k3_layout(d, d.hp8, K3_THREADS_MAX).total <= 232448 ? K3_THREADS_MAX : K3_THREADS_MIN;
+    const size_t cap = 232448;               // 227 KB of shared memory per CTA on sm_100
+    if (const char* e = getenv("JX_K3_THREADS")) {   // developer knob for A/B measurements
+        const int nt = atoi(e);
+        if ((nt == K3_NT_A || nt == K3_NT_B || nt == K3_NT_C) && k3_layout(d, d.hp8, nt).total <= cap) return nt;
+    }
+    if (k3_layout(d, d.hp8, K3_NT_A).total <= cap) return K3_NT_A;
+    if (k3_layout(d, d.hp8, K3_NT_B).total <= cap) return K3_NT_B;
+    return K3_NT_C;
 }
 
 cudaError_t jx_szmap_configure(const jx_dev& d) {
     const int nt = k3_pick_threads(d);
-    k3_smem_layout L = k3_layout(d, d.hp8, nt);
-    if (nt == K3_THREADS_MAX)
-        return cudaFuncSetAttribute(k3_szmap_kernel<K3_THREADS_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)L.total);
-    return cudaFuncSetAttribute(k3_szmap_kernel<K3_THREADS_MIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)L.total);
+    const int bytes = (int)k3_layout(d, d.hp8, nt).total;
+    const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    if (nt == K3_NT_A) return cudaFuncSetAttribute(k3_szmap_kernel<K3_NT_A>, at, bytes);
+    if (nt == K3_NT_B) return cudaFuncSetAttribute(k3_szmap_kernel<K3_NT_B>, at, bytes);
+    return cudaFuncSetAttribute(k3_szmap_kernel<K3_NT_C>, at, bytes);
 }
 
 size_t jx_szmap_smem_bytes(const jx_dev& d) { return k3_layout(d, d.hp8, k3_pick_threads(d)).total; }
@@ -344,13 +409,13 @@ cudaError_t jx_launch_szmap(const jx_dev& d, const double* coef, const uint32_t*
     if (W <= 0) return cudaSuccess;
     k3_args a;
     a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.g = g; a.scratch = nullptr;
+
     const int nt = k3_pick_threads(d);
-    k3_smem_layout L = k3_layout(d, d.hp8, nt);
-    int grid = W < sm_count ? W : sm_count;
-    if (nt == K3_THREADS_MAX)
-        k3_szmap_kernel<K3_THREADS_MAX><<<grid, K3_THREADS_MAX, L.total, st>>>(a);
-    else
-        k3_szmap_kernel<K3_THREADS_MIN><<<grid, K3_THREADS_MIN, L.total, st>>>(a);
+    const size_t bytes = k3_layout(d, d.hp8, nt).total;
+    const int grid = W < sm_count ? W : sm_count;
+    if (nt == K3_NT_A) k3_szmap_kernel<K3_NT_A><<<grid, K3_NT_A, bytes, st>>>(a);
+    else if (nt == K3_NT_B) k3_szmap_kernel<K3_NT_B><<<grid, K3_NT_B, bytes, st>>>(a);
+    else k3_szmap_kernel<K3_NT_C><<<grid, K3_NT_C, bytes, st>>>(a);
     return cudaGetLastError();
 }
 

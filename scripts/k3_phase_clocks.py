@@ -1,0 +1,65 @@
+"""Developer tool: SM cycles per phase of the map kernel (K3).
+
+Builds a private copy of the library with -DJX_K3_CLOCKS (build/libjoxsz_b200_clk.so), runs the shipped
+geometry with W walkers and prints the cycles per walker of phases A0 / A1 / B / C / D as seen by thread 0
+of each CTA.  Usage (on a GPU box): python scripts/k3_phase_clocks.py [W]
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from joxsz_b200 import build as jb, _lib  # noqa: E402
+
+
+def build_variant():
+    out = os.path.join(jb.HERE, "build", "libjoxsz_b200_clk.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    flags = [f for f in jb.NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    srcs = [os.path.join(jb.CSRC, s) for s in jb.SOURCES]
+    subprocess.check_call(["nvcc", *flags, "-DJX_K3_CLOCKS", "-shared", "-o", out, *srcs, "-lcudart"])
+    return out
+
+
+if __name__ == "__main__":
+    if "--build-only" in sys.argv:
+        print(build_variant())
+        sys.exit(0)
+    path = os.path.join(jb.HERE, "build", "libjoxsz_b200_clk.so")
+    if not os.path.exists(path):
+        build_variant()
+    _lib.LIB_PATH = path
+    import numpy as np
+    import torch
+    from joxsz_b200 import cluster
+    from joxsz_b200.batched import BatchedLikelihood
+    from joxsz_b200.mb import mb
+    from joxsz_b200.synthetic import draw_parameters
+
+    W = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 32768
+    mb.fit.debugfit = False
+    inp = cluster.load_inputs_npz(os.path.join(ROOT, "tests", "golden", "cl1226_inputs.npz"))
+    fit, _ = cluster.build_fit(inp, savedir=None)
+    eng = BatchedLikelihood(fit, max_walkers=W, device=0)
+    theta = torch.from_numpy(draw_parameters(fit.thawed, n=W, seed=4, spread=0.03, frac_bad=0.0)).cuda()
+    lib = _lib.load()
+    lib.jx_debug_k3_clocks.argtypes = [C.POINTER(C.c_ulonglong)]
+    out = (C.c_ulonglong * 8)()
+    for _ in range(3):
+        ll = eng(theta)
+    torch.cuda.synchronize()
+    lib.jx_debug_k3_clocks(out)
+    n = 5
+    for _ in range(n):
+        ll = eng(theta)
+    torch.cuda.synchronize()
+    lib.jx_debug_k3_clocks(out)
+    nfin = int(torch.isfinite(ll).sum()) if hasattr(ll, "sum") else int(np.isfinite(ll).sum())
+    names = ["A0 synth", "A1 rows", "B cols", "C rows", "D filter"]
+    tot = sum(out[i] for i in range(5))
+    print(f"walkers {W} (finite {nfin}), {n} launches; cycles per evaluated walker (thread 0 of its CTA):")
+    for i, nm in enumerate(names):
+        print(f"  {nm:10s} {out[i] / (n * W):10.0f}  {100.0 * out[i] / tot:5.1f} %")
+    print(f"  total      {tot / (n * W):10.0f}")
