@@ -310,8 +310,11 @@ def run_gpu_arm(args):
                 "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_walker": alg["szmap"], "walkers_per_launch": k3_walkers,
                 "avg_launch_ms": k3_avg_s * 1e3, "launches_timed": int(k3_n),
-                "note": "algorithmic bytes = staged maps of the reference (SURVEY 8d); the kernel keeps them in shared "
-                        "memory, so DRAM traffic is far below this and the binding limit is FP64 throughput",
+                "note": "algorithmic bytes = the maps of the stages this kernel replaces, materialised once (write y_2d, "
+                        "read y_2d, write the convolved map; SURVEY 8d convention); the kernel keeps them in shared "
+                        "memory and writes only the distinct pixels of the convolved map, so DRAM traffic is far below "
+                        "this and the binding limit is FP64 throughput.  The filter stage is the K7 GEMM "
+                        "(stage_rooflines.filter); stage_rooflines.szmap_plus_filter has both against the same bytes",
                 "fp64": {"alg_flops_per_walker": flops["szmap"], "measured_dfma_peak_tflops": tf.value, "measured_dmma_peak_tflops": tfd.value,
                          "achieved_tflops": flops["szmap"] * k3_walkers / k3_avg_s / 1e12 if k3_n else None}}
         ncalls = max(k3_n, 1)
@@ -334,8 +337,20 @@ def run_gpu_arm(args):
             return {"bound": "hbm", "alg_bytes_per_walker": alg[key], "ms": stage_ms[stage], "achieved_gbs": gbs,
                     "frac_of_measured_hbm": gbs / hbm_peak if gbs else None}
         proj_tf = flops["project"] * nw / (stage_ms["project"] * 1e-3) / 1e12 if stage_ms["project"] > 0 else None
+        filt_tf = flops["filter"] * nw / (stage_ms["filter"] * 1e-3) / 1e12 if stage_ms.get("filter", 0) > 0 else None
+        both_s = (stage_ms["szmap"] + stage_ms.get("filter", 0.0)) * 1e-3
+        both_gbs = alg["szmap"] * nw / both_s / 1e9 if both_s > 0 else None
         stage_roof = {"profiles": hbm("profiles", "profiles"), "szmap": hbm("szmap", "szmap"),
                       "xray": hbm("xray", "xray"), "tail": hbm("tail", "tail"),
+                      # the transfer-function filter is a GEMM over the walkers (K7) when the cyclic length is 256
+                      "filter": {"bound": "tensor(fp64 dmma)", "alg_flops_per_walker": flops["filter"],
+                                 "ms": stage_ms.get("filter"), "achieved_tflops": filt_tf,
+                                 "peak_tflops_measured_dmma": tfd.value,
+                                 "frac": filt_tf / tfd.value if filt_tf and tfd.value else None},
+                      # north_star item (3) as a whole: map synthesis + beam convolution + filtering
+                      "szmap_plus_filter": {"bound": "hbm", "alg_bytes_per_walker": alg["szmap"], "ms": both_s * 1e3,
+                                            "achieved_gbs": both_gbs,
+                                            "frac_of_measured_hbm": both_gbs / hbm_peak if both_gbs else None},
                       "project": {"bound": "tensor(fp64 dmma)", "alg_flops_per_walker": flops["project"],
                                   "ms": stage_ms["project"], "achieved_tflops": proj_tf,
                                   "peak_tflops_measured_dmma": tfd.value,

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define JX_ABI_VERSION 4
+#define JX_ABI_VERSION 5
 
 typedef enum jx_status {
     JX_OK = 0,
@@ -220,7 +220,7 @@ int jx_stretch_scatter(double* coords, double* lp, int32_t* naccept, const int32
                        void* stream);
 
 /* ---- measurement helpers (bench.py) */
-enum jx_stage { JX_ST_PROFILES = 0, JX_ST_PROJECT, JX_ST_SZMAP, JX_ST_XRAY, JX_ST_TAIL, JX_NSTAGE };
+enum jx_stage { JX_ST_PROFILES = 0, JX_ST_PROJECT, JX_ST_SZMAP, JX_ST_XRAY, JX_ST_TAIL, JX_ST_FILTER, JX_NSTAGE };
 /* When on, jx_loglike brackets each stage with CUDA events on `stream`. */
 int jx_set_profiling(jx_handle* h, int32_t on);
 /* Sum of per-stage device milliseconds and launch counts since the last reset [host outputs]; resets. */

@@ -8,10 +8,10 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-JX_ABI_VERSION = 4
+JX_ABI_VERSION = 5
 JX_NPAR = 19
-JX_NSTAGE = 5
-STAGE_NAMES = ("profiles", "project", "szmap", "xray", "tail")
+JX_NSTAGE = 6
+STAGE_NAMES = ("profiles", "project", "szmap", "xray", "tail", "filter")
 
 # slot order of include/joxsz_b200.h `enum jx_param_slot`, keyed by the reference's parameter names
 PARAM_SLOTS = (

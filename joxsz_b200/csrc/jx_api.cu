@@ -75,13 +75,13 @@ int check_ready(jx_handle* h, const double* theta, int W) {
 void flush_stage_events(jx_handle* h) {
     if (!h->pending) return;
     cudaEventSynchronize(h->ev[JX_NSTAGE]);
-    // execution order: profiles, xray, project, szmap, tail
-    static const int order[JX_NSTAGE] = {JX_ST_PROFILES, JX_ST_XRAY, JX_ST_PROJECT, JX_ST_SZMAP, JX_ST_TAIL};
+    // execution order: profiles, xray, project, szmap, filter, tail
+    static const int order[JX_NSTAGE] = {JX_ST_PROFILES, JX_ST_XRAY, JX_ST_PROJECT, JX_ST_SZMAP, JX_ST_FILTER, JX_ST_TAIL};
     for (int i = 0; i < JX_NSTAGE; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) {
             h->stage_ms[order[i]] += ms;
-            h->stage_launches[order[i]] += (order[i] == JX_ST_TAIL) ? 2 : 1;   // tail = row GEMM + K5
+            h->stage_launches[order[i]] += 1;     // one kernel per stage
         }
     }
     h->pending = false;
@@ -90,7 +90,7 @@ void flush_stage_events(jx_handle* h) {
 }  // namespace
 
 extern "C" const char* jx_build_info(void) {
-    return "libjoxsz_b200 abi=" "4" " arch=sm_100a fp64 K1=profiles K2=dmma-project K3=fft256-szmap(smem)|fft512/1024-szmap(L2) K4=xray K5=tail";
+    return "libjoxsz_b200 abi=" "5" " arch=sm_100a fp64 K1=profiles K2=dmma-project K3=fft256-szmap(smem)|fft512/1024-szmap(L2) K7=dmma-filter K4=xray K5=tail";
 }
 
 extern "C" const char* jx_last_error(const jx_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -312,6 +312,32 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
                 }
         rc = upload(h, &d.cfrag, t.data(), t.size());
     }
+    if (!rc && d.npad == 256) {
+        // filter stage as one GEMM (k7_filter.cu): response of map_out[N//2, N//2 + x] to the convolved-map pixel
+        // pair conv_c[u,v] = conv_c[v,u],
+        //   R[(u,v), x] = sum_kx (hf[u,kx] cmat[v,kx] + [u != v] hf[v,kx] cmat[u,kx]) dinv[kx, x],
+        // accumulated in long double so that the operator is correctly rounded to double
+        d.ntri = H * (H + 1) / 2;
+        d.ktri = (d.ntri + 31) & ~31;
+        std::vector<double> t((size_t)d.hp8 * d.ktri, 0.0);
+        std::vector<long double> f(H), dv((size_t)H * H);
+        for (int i = 0; i < H * H; ++i) dv[i] = (long double)s->dinv[i];
+        size_t idx = 0;
+        for (int u = 0; u < H; ++u)
+            for (int v = u; v < H; ++v, ++idx) {
+                for (int kx = 0; kx < H; ++kx) {
+                    long double e = (long double)s->hf[(size_t)u * H + kx] * (long double)s->cmat[(size_t)v * H + kx];
+                    if (u != v) e += (long double)s->hf[(size_t)v * H + kx] * (long double)s->cmat[(size_t)u * H + kx];
+                    f[kx] = e;
+                }
+                for (int x = 0; x < H; ++x) {
+                    long double acc = 0.0L;
+                    for (int kx = 0; kx < H; ++kx) acc += f[kx] * dv[(size_t)kx * H + x];
+                    t[(size_t)x * d.ktri + idx] = (double)acc;
+                }
+            }
+        rc = upload(h, &d.filt_op, t.data(), t.size());
+    }
     // workspace
     const size_t Wm = (size_t)s->max_walkers;
     if (!rc) rc = dev_alloc(h, &d.ws_pp, Wm * d.nrp);
@@ -324,7 +350,15 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     if (!rc) rc = dev_alloc(h, &d.ws_flags, Wm);
     if (!rc) rc = dev_alloc(h, &d.ws_coef, Wm * d.ncoef);
     if (!rc) rc = dev_alloc(h, &d.ws_row, Wm * d.nh);
-    if (!rc) rc = dev_alloc(h, &d.ws_g, Wm * d.hp8);
+    if (!rc && d.npad != 256) rc = dev_alloc(h, &d.ws_g, Wm * d.hp8);
+    if (!rc && d.npad == 256) {
+        rc = dev_alloc(h, &d.ws_tri, Wm * d.ktri);
+        // the columns beyond ntri are never written by the map kernel and must not hold NaN patterns (they meet
+        // zeros of filt_op); rows of walkers the map kernel skips are never read back
+        if (!rc && cudaMemset(d.ws_tri, 0, Wm * d.ktri * sizeof(double)) != cudaSuccess)
+            rc = fail(h, JX_ERR_CUDA, "cudaMemset(ws_tri)");
+        if (!rc) rc = dev_alloc(h, &d.ws_rowp, (size_t)jx_filter_parts(d) * Wm * d.hp8);
+    }
     if (!rc) {
         cudaError_t e = jx_profiles_configure(d);
         if (e == cudaSuccess) e = jx_gemm_configure();
@@ -334,9 +368,12 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
         size_t smem = jx_szmap_smem_bytes(d);
         if (smem > (size_t)prop.sharedMemPerBlockOptin) {
             rc = fail(h, JX_ERR_INVALID, "map kernel needs more shared memory than the device offers");
+        } else if (!jx_filter_supported(d)) {
+            rc = fail(h, JX_ERR_INVALID, "filter GEMM: map quarter plane wider than 136 pixels");
         } else {
             cudaError_t e = jx_szmap_configure(d);
-            if (e != cudaSuccess) rc = cuda_fail(h, e, "configure map kernel");
+            if (e == cudaSuccess) e = jx_filter_configure(d);
+            if (e != cudaSuccess) rc = cuda_fail(h, e, "configure map / filter kernels");
         }
     }
     if (!rc && d.npad != 256) {
@@ -357,12 +394,26 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     return JX_OK;
 }
 
-// map stage: shared-memory kernel when the cyclic length is 256, L2-staged kernel otherwise
-static cudaError_t launch_map(jx_handle* h, const double* coef, const uint32_t* flags, int W, double* convq,
-                              double* g, cudaStream_t st) {
+// Map stage + filter stage: spline coefficients -> map_out[N//2, N//2:] as `*nparts` partial rows at `*row`
+// (leading dimension `*ld_row`) for the tail kernel.  Cyclic length 256: shared-memory map kernel writing the packed
+// convolved map, then the filter GEMM over all walkers; 512 / 1024: L2-staged kernel with the filter stage inside,
+// then row = G . dinv.  `ev_mid`, when not NULL, is recorded between the two kernels (stage timers).
+static cudaError_t launch_map_filter(jx_handle* h, const double* coef, const uint32_t* flags, int W, double* convq,
+                                     const double** row, int* ld_row, int* nparts, cudaEvent_t ev_mid, cudaStream_t st) {
     const jx_dev& d = h->d;
-    if (d.npad == 256) return jx_launch_szmap(d, coef, flags, W, h->sm_count, convq, g, st);
-    return jx_launch_szmap_large(d, coef, flags, W, h->sm_count, convq, g, d.ws_scratch, st);
+    cudaError_t e;
+    if (d.npad == 256) {
+        e = jx_launch_szmap(d, coef, flags, W, h->sm_count, convq, d.ws_tri, st);
+        if (e == cudaSuccess && ev_mid) e = cudaEventRecord(ev_mid, st);
+        if (e != cudaSuccess) return e;
+        *row = d.ws_rowp; *ld_row = d.hp8; *nparts = jx_filter_parts(d);
+        return jx_launch_filter(d, d.ws_tri, W, d.ws_rowp, st);
+    }
+    e = jx_launch_szmap_large(d, coef, flags, W, h->sm_count, convq, d.ws_g, d.ws_scratch, st);
+    if (e == cudaSuccess && ev_mid) e = cudaEventRecord(ev_mid, st);
+    if (e != cudaSuccess) return e;
+    *row = d.ws_row; *ld_row = d.nh; *nparts = 1;
+    return jx_launch_gemm_nt(d.ws_g, d.hp8, d.dinv_t, d.hp8, d.ws_row, d.nh, W, d.nh, d.hp8, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -391,13 +442,14 @@ extern "C" int jx_loglike(jx_handle* h, const double* theta, int32_t W, double* 
     if (prof) JX_CUDA(h, cudaEventRecord(h->ev[2], st));
     JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op, d.ncoef, d.ws_coef, st));
     if (prof) JX_CUDA(h, cudaEventRecord(h->ev[3], st));
-    JX_CUDA(h, launch_map(h, d.ws_coef, d.ws_flags, W, nullptr, d.ws_g, st));
-    if (prof) JX_CUDA(h, cudaEventRecord(h->ev[4], st));
-    JX_CUDA(h, jx_launch_gemm_nt(d.ws_g, d.hp8, d.dinv_t, d.hp8, d.ws_row, d.nh, W, d.nh, d.hp8, st));
-    JX_CUDA(h, jx_launch_tail(d, theta, d.ws_row, d.ws_tsz, d.ws_flags, d.ws_prior, d.ws_xlike, d.ws_integ, W, nullptr,
-                              nullptr, nullptr, ll, st));
+    const double* row = nullptr;
+    int ld_row = 0, nparts = 1;
+    JX_CUDA(h, launch_map_filter(h, d.ws_coef, d.ws_flags, W, nullptr, &row, &ld_row, &nparts, prof ? h->ev[4] : nullptr, st));
+    if (prof) JX_CUDA(h, cudaEventRecord(h->ev[5], st));
+    JX_CUDA(h, jx_launch_tail(d, theta, row, ld_row, nparts, d.ws_tsz, d.ws_flags, d.ws_prior, d.ws_xlike, d.ws_integ, W,
+                              nullptr, nullptr, nullptr, ll, nullptr, st));
     if (prof) {
-        JX_CUDA(h, cudaEventRecord(h->ev[5], st));
+        JX_CUDA(h, cudaEventRecord(h->ev[6], st));
         h->pending = true;
     }
     return JX_OK;
@@ -457,7 +509,9 @@ extern "C" int jx_sz_maps(jx_handle* h, const double* theta, int32_t W, double* 
     if (y2d) JX_CUDA(h, jx_launch_tap_y2d(d, d.ws_coef, W, y2d, st));
     if (conv2d || mapout) {
         if ((rc = ensure_convq(h, W))) return rc;
-        JX_CUDA(h, launch_map(h, d.ws_coef, nullptr, W, d.ws_convq, d.ws_g, st));
+        const double* row = nullptr;
+        int ld_row = 0, nparts = 1;
+        JX_CUDA(h, launch_map_filter(h, d.ws_coef, nullptr, W, d.ws_convq, &row, &ld_row, &nparts, nullptr, st));
         if (conv2d) JX_CUDA(h, jx_launch_tap_expand(d, d.ws_convq, W, conv2d, st));
         if (mapout) {
             if (h->tap_scratch_walkers < (size_t)W) {
@@ -484,12 +538,12 @@ extern "C" int jx_sz_profile(jx_handle* h, const double* theta, int32_t W, doubl
     JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, d.ws_tsz, nullptr, nullptr, nullptr, nullptr, d.ws_integ,
                                   st));
     JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op, d.ncoef, d.ws_coef, st));
-    JX_CUDA(h, launch_map(h, d.ws_coef, nullptr, W, nullptr, d.ws_g, st));
-    JX_CUDA(h, jx_launch_gemm_nt(d.ws_g, d.hp8, d.dinv_t, d.hp8, d.ws_row, d.nh, W, d.nh, d.hp8, st));
-    JX_CUDA(h, jx_launch_tail(d, theta, d.ws_row, d.ws_tsz, nullptr, nullptr, nullptr, nullptr, W, bright, model, chisq,
-                              nullptr, st));
+    const double* rowp = nullptr;
+    int ld_row = 0, nparts = 1;
+    JX_CUDA(h, launch_map_filter(h, d.ws_coef, nullptr, W, nullptr, &rowp, &ld_row, &nparts, nullptr, st));
+    JX_CUDA(h, jx_launch_tail(d, theta, rowp, ld_row, nparts, d.ws_tsz, nullptr, nullptr, nullptr, nullptr, W, bright,
+                              model, chisq, nullptr, row, st));
     if (cint) JX_CUDA(h, cudaMemcpyAsync(cint, d.ws_integ, sizeof(double) * W, cudaMemcpyDeviceToDevice, st));
-    if (row) JX_CUDA(h, cudaMemcpyAsync(row, d.ws_row, sizeof(double) * W * d.nh, cudaMemcpyDeviceToDevice, st));
     return JX_OK;
 }
 

@@ -71,6 +71,9 @@ struct jx_dev {
     double integ_mu, integ_sig;
     const double* g_op_t;    // [nh, nd] g_op transposed (K5 reads it coalesced over the data points)
     const double* dinv_t;    // [nh(v), hp8(kx)] dinv transposed, zero padded: row = G . dinv as an NT GEMM
+    // filter stage as one GEMM over the walkers (cyclic length 256; k7_filter.cu)
+    int ntri, ktri;          // nh (nh + 1) / 2 pixels u <= v of the quarter plane; rounded up to 32
+    const double* filt_op;   // [hp8, ktri] zero padded: filt_op[x, (u,v)] = response of map_out[N//2, N//2 + x] to conv_c[u,v]
     // X-ray
     int na, nb, ntab;
     const double *midpt_kpc, *projvols, *tlog, *lnrate0, *lnrate1, *cts, *srcscale, *bkgterm;
@@ -87,7 +90,9 @@ struct jx_dev {
     uint32_t* ws_flags; // [W]
     double* ws_coef;    // [W, ncoef]
     double* ws_row;     // [W, nh]  map_out[N//2, N//2:]
-    double* ws_g;       // [W, hp8] G[kx] written by the map kernel
+    double* ws_g;       // [W, hp8] G[kx] written by the large-map kernel
+    double* ws_tri;     // [W, ktri] packed triangle of the convolved map (map kernel -> filter GEMM), zero padded
+    double* ws_rowp;    // [jx_filter_parts(d) * W, hp8] K-split partial sums of the filter GEMM
     double* ws_convq;   // tap only, allocated lazily: [W, nh, nh]
 };
 
@@ -127,11 +132,19 @@ cudaError_t jx_launch_gemm_nt(const double* A, int lda, const double* B, int ldb
 // production map stage: coef -> G[kx] (+ optional quarter-plane convolved map).  `flags` may be NULL
 // (evaluate every walker); flagged walkers are skipped.
 cudaError_t jx_launch_szmap(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
-                            double* convq, double* g, cudaStream_t st);
-// tail: row -> bright, model, chisq, ll (any output may be NULL)
-cudaError_t jx_launch_tail(const jx_dev& d, const double* theta, const double* row, const double* tsz,
-                           const uint32_t* flags, const double* prior, const double* xlike, const double* cint, int W,
-                           double* bright, double* model, double* chisq, double* ll, cudaStream_t st);
+                            double* convq, double* tri, cudaStream_t st);
+// filter stage (k7_filter.cu): rowp[kparts][W][hp8] = K-split partial sums of tri[W, ktri] . filt_op^T
+constexpr int JX_FILTER_CPP = 13;         // chunks of 32 packed pixels per K part
+bool jx_filter_supported(const jx_dev& d);
+cudaError_t jx_filter_configure(const jx_dev& d);
+int jx_filter_parts(const jx_dev& d);     // ws_rowp holds jx_filter_parts(d) * max_walkers rows
+cudaError_t jx_launch_filter(const jx_dev& d, const double* tri, int W, double* rowp, cudaStream_t st);
+// tail: row -> bright, model, chisq, ll (any output may be NULL).  row = sum of `nparts` partial rows,
+// part p at row + p * W * ld_row.
+cudaError_t jx_launch_tail(const jx_dev& d, const double* theta, const double* row, int ld_row, int nparts,
+                           const double* tsz, const uint32_t* flags, const double* prior, const double* xlike,
+                           const double* cint, int W, double* bright, double* model, double* chisq, double* ll,
+                           double* row_out, cudaStream_t st);
 cudaError_t jx_szmap_configure(const jx_dev& d);   // one-time cudaFuncSetAttribute
 cudaError_t jx_launch_tap_y2d(const jx_dev& d, const double* coef, int W, double* y2d, cudaStream_t st);
 cudaError_t jx_launch_tap_expand(const jx_dev& d, const double* convq, int W, double* conv2d, cudaStream_t st);

@@ -11,7 +11,8 @@ struct k3_args {
     const double* coef;
     const uint32_t* flags;
     int W;
-    double *convq, *g;
+    double *convq, *g;    // g: large-map path (filter stage in the kernel); convq: parity tap
+    double* tri;          // shared-memory path: packed u <= v triangle of the convolved map, [W][d.ktri]
     double* scratch;      // large-map path only: [gridDim.x][hp8][pitch] doubles
 };
 
@@ -141,112 +142,3 @@ JX_D int k3_run_phase_d(const jx_dev& d, const double* xs, int pitch, double* gp
 }
 
 
-// ---- phase D, flat schedule (map kernel with the whole convolved map in shared memory, at most 12 u-tiles) -----------
-// A DMMA of one warp occupies the FP64 tensor pipe of its scheduler for 16 cycles but the warp only issues the next
-// one ~64 cycles later, so the pipe needs four busy warps per scheduler, all with the same amount of work.  The work
-// is therefore cut into units (kx tile jt, k step ks) of NUT DMMAs each (every u-tile), numbered L = jt * nks + ks,
-// and warp w takes the contiguous range [w T / nw, (w+1) T / nw): equal shares whatever the tile count.  A range
-// that crosses into the next kx tile ends a segment: the accumulators are folded with hf into an 8-wide partial
-// G and restarted.  Partials go to gpart_s[(warp * JX_DF_MAXSEG + seg) * 8 ..] with the tile number in
-// segjt_s[warp * JX_DF_MAXSEG + seg] (-1 = unused); the caller adds them in slot order (deterministic).
-constexpr int JX_DF_MAXSEG = 3;
-
-struct k3_dflat_state {
-    int L, L1;
-    double bq[4];
-};
-
-// range of this warp and the first B fragments of its first segment (constants only: may run before the barrier
-// that publishes the convolved map)
-JX_D k3_dflat_state k3_dflat_begin(const jx_dev& d, int warp, int lane, int nwarps) {
-    const int ntile = d.hp8 >> 3, nks = d.hp8 >> 2, T = ntile * nks;
-    k3_dflat_state st;
-    st.L = (int)(((long long)warp * T) / nwarps);
-    st.L1 = (int)(((long long)(warp + 1) * T) / nwarps);
-    const int jt = st.L / nks, ks = st.L - jt * nks;
-    const int end = min(nks, ks + (st.L1 - st.L));
-    const double* bp = d.cfrag + (size_t)jt * nks * 32 + lane;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) st.bq[q] = ks + q < end ? __ldg(bp + (ks + q) * 32) : 0.0;
-    return st;
-}
-
-template <int NUT>
-JX_D void k3_dflat_run(const jx_dev& d, const double* __restrict__ xs, int ld, k3_dflat_state st,
-                       double* __restrict__ gpart_s, int* __restrict__ segjt_s, int warp, int lane) {
-    const int hp8 = d.hp8, nks = hp8 >> 2;
-    const int frow = lane >> 2, fk = lane & 3;
-    const int voff = (fk & 1) + 4 * (fk >> 1);          // k permutation of k3_phase_d
-    const double* arow = xs + (size_t)frow * ld + voff;
-    int L = st.L, seg = 0;
-    double bq[4] = {st.bq[0], st.bq[1], st.bq[2], st.bq[3]};
-    while (L < st.L1) {
-        const int jt = L / nks, ks_a = L - jt * nks;
-        const int ks_b = min(nks, ks_a + (st.L1 - L));
-        const double* bp = d.cfrag + (size_t)jt * nks * 32 + lane;
-        if (seg) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) bq[q] = ks_a + q < ks_b ? __ldg(bp + (ks_a + q) * 32) : 0.0;
-        }
-        double acc[NUT][2];
-#pragma unroll
-        for (int i = 0; i < NUT; ++i) acc[i][0] = acc[i][1] = 0.0;
-        for (int ks0 = ks_a; ks0 < ks_b; ks0 += 4) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int ks = ks0 + q;
-                if (ks < ks_b) {                         // warp-uniform
-                    const double b = bq[q];
-                    if (ks + 4 < ks_b) bq[q] = __ldg(bp + (ks + 4) * 32);
-                    const double* ap = arow + 8 * (ks >> 1) + 2 * (ks & 1);
-                    double af[NUT];
-#pragma unroll
-                    for (int i = 0; i < NUT; ++i) af[i] = ap[(size_t)i * 8 * ld];
-#pragma unroll
-                    for (int i = 0; i < NUT; ++i) dmma884(acc[i][0], acc[i][1], af[i], b);
-                }
-            }
-        }
-        // fold in hf[u, kx] and reduce over the 8 fragment rows
-        double g0 = 0.0, g1 = 0.0;
-        const int kc = jt * 8 + 2 * fk;
-#pragma unroll
-        for (int i = 0; i < NUT; ++i) {
-            const double2 h = __ldg(reinterpret_cast<const double2*>(d.hf_pad + (size_t)(i * 8 + frow) * hp8 + kc));
-            g0 += acc[i][0] * h.x;
-            g1 += acc[i][1] * h.y;
-        }
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-            g0 += __shfl_xor_sync(0xffffffffu, g0, o);
-            g1 += __shfl_xor_sync(0xffffffffu, g1, o);
-        }
-        const int slot = warp * JX_DF_MAXSEG + seg;
-        if (lane < 4) {
-            gpart_s[slot * 8 + 2 * fk] = g0;
-            gpart_s[slot * 8 + 2 * fk + 1] = g1;
-        }
-        if (lane == 0) segjt_s[slot] = jt;
-        L += ks_b - ks_a;
-        ++seg;
-    }
-    if (lane == 0)
-        for (; seg < JX_DF_MAXSEG; ++seg) segjt_s[warp * JX_DF_MAXSEG + seg] = -1;
-}
-
-// the flat schedule applies when one warp can hold every u-tile and no range spans more than JX_DF_MAXSEG kx tiles
-JX_HD bool k3_dflat_ok(int hp8, int nwarps) {
-    const int ntile = hp8 >> 3, nks = hp8 >> 2, T = ntile * nks;
-    return ntile <= 12 && (T + nwarps - 1) / nwarps <= (JX_DF_MAXSEG - 1) * nks;
-}
-
-JX_D void k3_run_phase_d_flat(const jx_dev& d, const double* xs, int ld, const k3_dflat_state& st, double* gpart_s,
-                              int* segjt_s, int warp, int lane) {
-    switch (d.hp8 >> 3) {
-#define JX_D_CASE(n) case n: k3_dflat_run<n>(d, xs, ld, st, gpart_s, segjt_s, warp, lane); break;
-        JX_D_CASE(1) JX_D_CASE(2) JX_D_CASE(3) JX_D_CASE(4) JX_D_CASE(5) JX_D_CASE(6)
-        JX_D_CASE(7) JX_D_CASE(8) JX_D_CASE(9) JX_D_CASE(10) JX_D_CASE(11) JX_D_CASE(12)
-#undef JX_D_CASE
-        default: break;
-    }
-}

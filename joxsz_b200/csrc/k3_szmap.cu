@@ -1,10 +1,7 @@
-// K3 (+K5) -- Compton-y map synthesis, beam convolution, transfer-function filtering and the
-// chi-square tail, one persistent CTA per SM looping over walkers; the whole map pipeline of a walker
-// lives in shared memory.
+// K3 -- Compton-y map synthesis and beam convolution, one persistent CTA per SM looping over walkers; the
+// whole map pipeline of a walker lives in shared memory.
 //
-// Replaces, per walker, reference joxsz_funcs.py:462 (y_2d = f(d_mat)), :464 (fftconvolve 'same'),
-// :466-467 (fft2 * filtering, ifft2), :469-479 (T_SZ conversion, calibration, spline to the data radii,
-// chi^2) and :538 (sum of the three terms).
+// Replaces, per walker, reference joxsz_funcs.py:462 (y_2d = f(d_mat)) and :464 (fftconvolve 'same').
 //
 // Geometry facts used (checked at pack time, joxsz_b200/operators.py): the map side N is odd and the
 // Compton-y map, the beam and the filter are symmetric under x -> -x, y -> -y about the centre pixel.
@@ -14,13 +11,12 @@
 //
 //   A  rows    Z[u,:]  (spline pieces evaluated on the fly)  --FFT256-->  xs[u, kx]      kx = 0..P/2
 //   B  columns xs[:, kx] --FFT256--> * bhat[ky, kx] --FFT256--> xs[u, kx]            (beam, cyclic length P)
-//   C  rows    xs[u, :]  --FFT256--> conv_c[u, v]  (in place)     = fftconvolve(y_2d, beam,'same')*step^2
-//   D  G[kx] = sum_u hf[u,kx] * sum_v conv_c[u,v] w_v cos(2 pi kx v / N)      FP64 tensor cores (DMMA)
-// and the kernel writes G[kx] (H doubles per walker).  The remaining steps are batched over walkers outside
-// this kernel: row = G . dinv (one small DMMA GEMM, k2_project.cu) and the conversion / chi^2 tail (k5_tail.cu).
-//
-// D+E are the exact length-N circular filter (N = 171 = 9*19 for the shipped cluster, so a dense
-// cosine transform), reduced over ky analytically because only the central row is consumed.
+//   C  rows    xs[u, :]  --FFT256--> conv_c[u, v]                = fftconvolve(y_2d, beam,'same')*step^2
+// and the kernel writes conv_c on u <= v (the convolved map is symmetric under x <-> y as well), packed row-major,
+// H (H + 1) / 2 doubles per walker, straight from the registers of phase C.  The remaining steps are batched over
+// walkers outside this kernel: the exact length-N circular filter (N = 171 = 9*19 for the shipped cluster, no fast
+// transform) restricted to the consumed row is one DMMA GEMM with a constant operator (k7_filter.cu), then the
+// conversion / chi^2 tail (k5_tail.cu).
 // The per-walker inputs (spline coefficients) arrive by TMA bulk copy (cp.async.bulk + mbarrier),
 // double buffered against the previous walker's compute.
 #include "k3_common.cuh"
@@ -54,7 +50,7 @@ constexpr int K3_Q = K3_P / 2 + 1;       // 129
 constexpr int K3_XS = 130;               // row pitch of xs (doubles): XS/2 odd -> conflict-free column walks
 
 struct k3_smem_layout {
-    size_t tw, xbuf, xs, coef, gpart, segjt, mbar, total;
+    size_t tw, xbuf, xs, coef, mbar, total;
 };
 
 __host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8, int nthreads) {
@@ -65,11 +61,6 @@ __host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8, in
     L.xbuf = take((size_t)(nthreads / 32) * 3 * JX_XE_ELEMS * sizeof(double2));
     L.xs = take((size_t)hp8 * K3_XS * sizeof(double));
     L.coef = take((size_t)2 * d.ncoef * sizeof(double));
-    {
-        const size_t split = (size_t)JX_D_MAXSPLIT * hp8, flat = (size_t)(nthreads / 32) * JX_DF_MAXSEG * 8;
-        L.gpart = take((split > flat ? split : flat) * sizeof(double));
-    }
-    L.segjt = take((size_t)(nthreads / 32) * JX_DF_MAXSEG * sizeof(int));
     L.mbar = take(2 * sizeof(uint64_t));
     L.total = o;
     return L;
@@ -79,15 +70,12 @@ template <int NT>
 __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__ k3_args a) {
     extern __shared__ __align__(128) unsigned char k3_raw[];
     const jx_dev& d = a.d;
-    const int H = d.nh, hp8 = d.hp8, hp16 = d.hp16;
+    const int H = d.nh, hp8 = d.hp8;
     const k3_smem_layout L = k3_layout(d, hp8, NT);
     double2* tw_s = reinterpret_cast<double2*>(k3_raw + L.tw);
     double2* xbuf_all = reinterpret_cast<double2*>(k3_raw + L.xbuf);
     double* xs = reinterpret_cast<double*>(k3_raw + L.xs);
     double* coef_s = reinterpret_cast<double*>(k3_raw + L.coef);
-    double* gpart_s = reinterpret_cast<double*>(k3_raw + L.gpart);
-    int* segjt_s = reinterpret_cast<int*>(k3_raw + L.segjt);
-    const bool dflat = false && k3_dflat_ok(hp8, NT / 32);   // measured slower than one kx tile per warp here
     uint64_t* mbar = reinterpret_cast<uint64_t*>(k3_raw + L.mbar);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -146,7 +134,7 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
         // pixel (u, v) also fills (v, u); the table lists u <= v in thread order (one coalesced 16-byte load
         // per pixel, all of a thread's loads in flight together).
         {
-            constexpr int A0_UNROLL = 5;
+            constexpr int A0_UNROLL = 8;
             const int4* tab = reinterpret_cast<const int4*>(d.synth);
             for (int base = 0; base < d.nsynth; base += A0_UNROLL * NT) {
                 int4 e[A0_UNROLL];
@@ -243,7 +231,10 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
         __syncthreads();
         K3_CLK(2);
 
-        // ================= phase C: rows back to pixel space, in place: xs[u, v] = conv_c[u, v]
+        // ================= phase C: rows back to pixel space; conv_c[u, v] for v >= u goes to the packed triangle
+        // of this walker (row u starts at u H - u (u - 1) / 2), 72-byte runs per (row, register position)
+        double* tri_w = a.tri + (size_t)w * d.ktri;
+        const bool tap = a.convq != nullptr;                  // parity tap: also keep the full quarter plane
         for (int base = warp * 3; base < npair; base += 3 * NW) {
             const bool ok = lane_on && base + fg < npair;
             const int u0 = 2 * (base + fg < npair ? base + fg : npair - 1), u1 = u0 + 1;
@@ -257,53 +248,32 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
             fft256e_pass1(t, re, im, tw_s, xbuf);
             __syncwarp();
             fft256_pass2(t, re, im, xbuf);
-            // every lane of the warp has read its row pair: the in-place stores below cannot overtake them
-            __syncwarp();
+            double* tri0 = tri_w + (u0 * H - ((u0 * (u0 - 1)) >> 1) - u0);     // + v
+            double* tri1 = tri0 + (H - u0 - 1);                                 // row u1: off(u0) + (H - u0) - u1
+            if (tap) __syncwarp();   // every lane of the warp has read its row pair before the in-place stores
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
                 const int n = t + 16 * rev16(p);
                 const int v = fold256(n);
-                if (ok && v < hp16 && !(n > 128 && t_edge)) {
-                    const bool in = v < H;
-                    xs[u0 * K3_XS + v] = in ? re[p] : 0.0;
-                    if (has1) xs[u1 * K3_XS + v] = in ? im[p] : 0.0;
+                if (ok && v < H && !(n > 128 && t_edge)) {
+                    if (v >= u0) tri0[v] = re[p];
+                    if (has1 && v >= u1) tri1[v] = im[p];
+                    if (tap) {
+                        xs[u0 * K3_XS + v] = re[p];
+                        if (has1) xs[u1 * K3_XS + v] = im[p];
+                    }
                 }
             }
         }
-        // phase D's first cosine fragments come from L2: start them before waiting for the other warps
-        k3_dflat_state dst;
-        if (dflat) dst = k3_dflat_begin(d, warp, lane, NT / 32);
-        __syncthreads();
+        __syncthreads();        // all reads of xs are done: the next walker's synthesis (or the tap) may proceed
         K3_CLK(3);
 
-        if (a.convq) {
+        if (tap) {
             double* cq = a.convq + (size_t)w * H * H;
             for (int i = tid; i < H * H; i += NT) cq[i] = xs[(i / H) * K3_XS + (i % H)];
-        }
-
-        // ================= phase D: G[kx] = sum_u hf[u,kx] sum_v conv_c[u,v] w_v cos(2 pi kx v/N)   (DMMA)
-        // G[kx] leaves the kernel; row = G . dinv and the tail are batched over walkers afterwards
-        if (dflat) {
-            k3_run_phase_d_flat(d, xs, K3_XS, dst, gpart_s, segjt_s, warp, lane);
+            // the next iteration's first barrier is after its synthesis writes: order the tap reads before them
             __syncthreads();
-            if (tid < hp8) {
-                const int jt = tid >> 3, c = tid & 7;
-                double g = 0.0;
-                for (int sl = 0; sl < (NT / 32) * JX_DF_MAXSEG; ++sl)
-                    if (segjt_s[sl] == jt) g += gpart_s[sl * 8 + c];
-                a.g[(size_t)w * hp8 + tid] = g;
-            }
-        } else {
-            const int nsplit = k3_run_phase_d<K3_XS>(d, xs, K3_XS, gpart_s, warp, lane, NT / 32);
-            __syncthreads();
-            if (tid < hp8) {
-                double g = gpart_s[tid];
-                for (int p = 1; p < nsplit; ++p) g += gpart_s[p * hp8 + tid];
-                a.g[(size_t)w * hp8 + tid] = g;
-            }
         }
-        K3_CLK(4);
-        // the next iteration's first barrier orders these reads of gpart_s / xs before they are rewritten
     }
 }
 
@@ -405,10 +375,10 @@ cudaError_t jx_szmap_configure(const jx_dev& d) {
 size_t jx_szmap_smem_bytes(const jx_dev& d) { return k3_layout(d, d.hp8, k3_pick_threads(d)).total; }
 
 cudaError_t jx_launch_szmap(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
-                            double* convq, double* g, cudaStream_t st) {
+                            double* convq, double* tri, cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
     k3_args a;
-    a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.g = g; a.scratch = nullptr;
+    a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.g = nullptr; a.tri = tri; a.scratch = nullptr;
 
     const int nt = k3_pick_threads(d);
     const size_t bytes = k3_layout(d, d.hp8, nt).total;

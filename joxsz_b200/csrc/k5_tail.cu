@@ -8,7 +8,8 @@
 //   chisq  = nansum(((flux - model) / err)^2);  ll = (xray + prior) - chisq / 2  (:478-479, :536-538)
 //   with calc_integ: ll -= nansum(((cint - mu) / sig)^2) / 2, cint from K1       (:480-485)
 //
-// `row` = map_out[N//2, N//2:] comes from the map kernel's G vector through one small GEMM (jx_api.cu).
+// `row` = map_out[N//2, N//2:] comes from the filter GEMM (k7_filter.cu) as `nparts` K-split partial rows that
+// are added here in order, or from the large-map kernel's G vector through one small GEMM (jx_api.cu).
 // Walkers whose status bits are set get ll = -inf (the reference returns before / regardless of this
 // stage, joxsz_funcs.py:519-520, 523-525, 529-532, 536).
 #include "jx_common.cuh"
@@ -21,8 +22,8 @@ struct k5_args {
     jx_dev d;
     const double *theta, *row, *tsz, *prior, *xlike, *cint;
     const uint32_t* flags;
-    int W;
-    double *bright, *model, *chisq, *ll;
+    int W, ld_row, nparts;
+    double *bright, *model, *chisq, *ll, *row_out;
 };
 
 // scipy interp1d(kind='linear', fill_value='extrapolate') on a small table
@@ -56,10 +57,14 @@ __global__ void __launch_bounds__(K5_WARPS * 32) k5_tail_kernel(const __grid_con
 
     const int csrc = d.slot_src[JX_CALIB];
     const double calib = csrc < 0 ? d.slot_val[JX_CALIB] : a.theta[(size_t)w * d.ndim + csrc];
-    const double* row = a.row + (size_t)w * H;
+    const double* row = a.row + (size_t)w * a.ld_row;
+    const size_t part_stride = (size_t)a.W * a.ld_row;
     for (int v = lane; v < H; v += 32) {
         const double T = v == 0 ? T0 : tsz[v - 1];
-        const double br = row[v] * linear_extrap(T, d.conv_T, d.conv_I, d.nconv) * calib;
+        double r = row[v];
+        for (int p = 1; p < a.nparts; ++p) r += row[p * part_stride + v];
+        if (a.row_out) a.row_out[(size_t)w * H + v] = r;
+        const double br = r * linear_extrap(T, d.conv_T, d.conv_I, d.nconv) * calib;
         bright_s[v] = br;
         if (a.bright) a.bright[(size_t)w * H + v] = br;
     }
@@ -100,11 +105,12 @@ __global__ void __launch_bounds__(K5_WARPS * 32) k5_tail_kernel(const __grid_con
 
 }  // namespace
 
-cudaError_t jx_launch_tail(const jx_dev& d, const double* theta, const double* row, const double* tsz,
-                           const uint32_t* flags, const double* prior, const double* xlike, const double* cint, int W,
-                           double* bright, double* model, double* chisq, double* ll, cudaStream_t st) {
+cudaError_t jx_launch_tail(const jx_dev& d, const double* theta, const double* row, int ld_row, int nparts,
+                           const double* tsz, const uint32_t* flags, const double* prior, const double* xlike,
+                           const double* cint, int W, double* bright, double* model, double* chisq, double* ll,
+                           double* row_out, cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
-    k5_args a{d, theta, row, tsz, prior, xlike, cint, flags, W, bright, model, chisq, ll};
+    k5_args a{d, theta, row, tsz, prior, xlike, cint, flags, W, ld_row, nparts, bright, model, chisq, ll, row_out};
     const size_t smem = (size_t)K5_WARPS * d.nh * sizeof(double);
     k5_tail_kernel<<<(W + K5_WARPS - 1) / K5_WARPS, K5_WARPS * 32, smem, st>>>(a);
     return cudaGetLastError();

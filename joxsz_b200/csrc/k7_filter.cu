@@ -1,0 +1,169 @@
+// K7 -- transfer-function filtering of the beam-convolved map as ONE dense FP64 contraction over all walkers.
+//
+// Replaces, for every walker of the batch, reference joxsz_funcs.py:466-467
+//     map_out = real(ifft2(fft2(conv) * filtering))
+// restricted to the part the likelihood consumes, map_out[N//2, N//2:] (:472).  The circular filter at the exact
+// map size N (171 = 9 * 19 for the shipped cluster: no fast transform) is linear, and the convolved map is
+// symmetric under x <-> y, x -> -x, y -> -y, so the H = N//2 + 1 consumed values are a fixed linear map of the
+// H (H + 1) / 2 distinct pixels u <= v of the quarter plane:
+//
+//     row[w, x] = sum_{u <= v} tri[w, (u, v)] R[(u, v), x]
+//     R[(u, v), x] = sum_kx (hf[u,kx] cmat[v,kx] + [u != v] hf[v,kx] cmat[u,kx]) dinv[kx, x]     (built at jx_create)
+//
+// with hf = filter folded with the k_y cosine sum, cmat = w_v cos(2 pi kx v / N), dinv = inverse cosine transform
+// of the row (joxsz_b200/operators.py).  `tri` is what the map kernel (k3_szmap.cu) writes: the convolved map
+// fftconvolve(y_2d, beam, 'same') * step^2 (:464) on u <= v, row-major packed, zero padded to a multiple of 32.
+// Half the flops of transforming every row of the quarter plane (K = H(H+1)/2 instead of H^2), and a regular
+// GEMM with a constant, L2-resident B operand instead of a per-walker one.
+//
+// FP64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA): the 1e-6 absolute bar on the log-likelihood needs double
+// operands and accumulation, and tcgen05 has no f64 kind.
+//
+// Tiling: CTA = 128 walkers x all 8 NT outputs, 8 warps, warp tile 16 x 8 NT (2 x NT DMMA tiles), K in chunks
+// of 32 through a 3-stage cp.async ring (rows padded to 36 doubles: both fragment loads take the minimum two
+// wavefronts).  K is additionally split into contiguous parts of JX_FILTER_CPP chunks (grid.x) so that walker tiles
+// x parts fills the SMs evenly; part p writes its partial sums to C + p * M * ldc and the tail kernel
+// (k5_tail.cu) adds the parts in order -- deterministic, no atomics, independent of the batch size.
+#include "jx_common.cuh"
+
+namespace {
+
+constexpr int K7_BM = 128, K7_BK = 32, K7_LDS = K7_BK + 4, K7_STAGES = 3, K7_THREADS = 256;
+
+JX_D void k7_cp16(void* smem, const void* gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
+}
+JX_D void k7_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+JX_D void k7_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+JX_D void k7_dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int NT>
+constexpr size_t k7_smem_bytes() { return (size_t)K7_STAGES * (K7_BM + 8 * NT) * K7_LDS * sizeof(double); }
+
+// A: [M, lda] packed convolved maps (lda = K rounded up to 32, zero padded), B: [8 NT, lda] = R^T zero padded,
+// C: [kparts][M][8 NT]
+template <int NT>
+__global__ void __launch_bounds__(K7_THREADS, 1)
+k7_filter_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int lda, int M,
+                      int nchunks_total, int chunks_per_part) {
+    extern __shared__ __align__(16) double k7_smem[];
+    constexpr int BN = 8 * NT;
+    double* As = k7_smem;                                          // [STAGES][BM][LDS]
+    double* Bs = k7_smem + (size_t)K7_STAGES * K7_BM * K7_LDS;     // [STAGES][BN][LDS]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int part = blockIdx.x, m0 = blockIdx.y * K7_BM;
+    const int c_first = part * chunks_per_part;
+    const int nchunks = min(chunks_per_part, nchunks_total - c_first);
+
+    auto load_stage = [&](int stage, int chunk) {
+        const int k0 = (c_first + chunk) * K7_BK;
+#pragma unroll
+        for (int it = 0; it < (K7_BM * K7_BK / 2) / K7_THREADS; ++it) {
+            const int piece = it * K7_THREADS + tid;
+            const int row = piece >> 4, col = (piece & 15) * 2;
+            const bool ok = m0 + row < M;
+            k7_cp16(As + ((size_t)stage * K7_BM + row) * K7_LDS + col, A + (size_t)(ok ? m0 + row : 0) * lda + k0 + col, ok);
+        }
+#pragma unroll
+        for (int it = 0; it < (BN * K7_BK / 2 + K7_THREADS - 1) / K7_THREADS; ++it) {
+            const int piece = it * K7_THREADS + tid;
+            if (piece < BN * K7_BK / 2) {
+                const int row = piece >> 4, col = (piece & 15) * 2;
+                k7_cp16(Bs + ((size_t)stage * BN + row) * K7_LDS + col, B + (size_t)row * lda + k0 + col, true);
+            }
+        }
+    };
+
+    double acc[2][NT][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int s = 0; s < K7_STAGES - 1; ++s) {
+        if (s < nchunks) load_stage(s, s);
+        k7_commit();
+    }
+    const int frow = lane >> 2, fk = lane & 3;
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        k7_wait<K7_STAGES - 2>();
+        __syncthreads();
+        const int next = chunk + K7_STAGES - 1;          // reuses the slot consumed in the previous iteration
+        if (next < nchunks) load_stage(next % K7_STAGES, next);
+        k7_commit();
+        const double* as = As + ((size_t)(chunk % K7_STAGES) * K7_BM + warp * 16 + frow) * K7_LDS + fk;
+        const double* bs = Bs + ((size_t)(chunk % K7_STAGES) * BN + frow) * K7_LDS + fk;
+#pragma unroll
+        for (int kk = 0; kk < K7_BK; kk += 4) {
+            double bf[NT];
+            const double a0 = as[kk], a1 = as[(size_t)8 * K7_LDS + kk];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) bf[j] = bs[(size_t)j * 8 * K7_LDS + kk];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                k7_dmma(acc[0][j][0], acc[0][j][1], a0, bf[j]);
+                k7_dmma(acc[1][j][0], acc[1][j][1], a1, bf[j]);
+            }
+        }
+    }
+    k7_wait<0>();
+
+    // lane owns C[row = lane / 4][col = 2 (lane % 4) + {0, 1}] of each 8 x 8 tile
+    double* Cp = C + (size_t)part * M * BN;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + warp * 16 + i * 8 + frow;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+            *reinterpret_cast<double2*>(Cp + (size_t)m * BN + j * 8 + 2 * fk) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+}
+
+#define K7_FOR_NT(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17)
+
+}  // namespace
+
+// largest map quarter plane the kernel is instantiated for: 8 * 17 >= 129, the most a cyclic length of 256 admits
+bool jx_filter_supported(const jx_dev& d) { return d.hp8 / 8 >= 1 && d.hp8 / 8 <= 17; }
+
+cudaError_t jx_filter_configure(const jx_dev& d) {
+    const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    switch (d.hp8 / 8) {
+#define K7_CASE(n) case n: return cudaFuncSetAttribute(k7_filter_gemm_kernel<n>, at, (int)k7_smem_bytes<n>());
+        K7_FOR_NT(K7_CASE)
+#undef K7_CASE
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// Number of K parts: fixed by the geometry alone (JX_FILTER_CPP chunks of 32 per part), never by the batch size,
+// so that a walker's result does not depend on which batch it is evaluated in (the sampler's chains are
+// bit-identical for any number of ranks).  117 chunks -> 9 parts for the shipped cluster: 256 walker tiles x 9
+// parts fill 148 SMs to 97 %.
+int jx_filter_parts(const jx_dev& d) {
+    const int nchunks = d.ktri / K7_BK;
+    return (nchunks + JX_FILTER_CPP - 1) / JX_FILTER_CPP;
+}
+
+// rowp[kparts][W][hp8] = partial sums of tri[W, ktri] . filt_op[hp8, ktri]^T
+cudaError_t jx_launch_filter(const jx_dev& d, const double* tri, int W, double* rowp, cudaStream_t st) {
+    if (W <= 0) return cudaSuccess;
+    const int nchunks = d.ktri / K7_BK, cpp = JX_FILTER_CPP;
+    dim3 grid(jx_filter_parts(d), (W + K7_BM - 1) / K7_BM);
+    switch (d.hp8 / 8) {
+#define K7_CASE(n) case n: k7_filter_gemm_kernel<n><<<grid, K7_THREADS, k7_smem_bytes<n>(), st>>>( \
+                               tri, d.filt_op, rowp, d.ktri, W, nchunks, cpp); break;
+        K7_FOR_NT(K7_CASE)
+#undef K7_CASE
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}

@@ -280,5 +280,12 @@ class PackedSetup:
         lg = math.log2
         return {
             "project": 2.0 * nr * 4 * self.map_ops.nseg,
-            "szmap": 2 * 5 * pd * pd * lg(pd * pd) + 2 * 5 * N * N * lg(N * N) + 6 * pd * pd + 6 * N * N,
+            # filter stage: one GEMM row of K = H (H + 1) / 2 distinct convolved-map pixels by H outputs when the
+            # cyclic length is 256 (k7_filter.cu); the large-map kernel transforms all H rows instead
+            "filter": (2.0 * (self.H * (self.H + 1) // 2) * self.H if pd == 256 else 2.0 * self.H ** 3),
+            # SURVEY 8(d) convention (full complex FFTs): padded convolution + exact-size filter.  The shared-memory
+            # map kernel (cyclic length 256) ends at the convolved map, so only the first half is its own
+            "szmap": (2 * 5 * pd * pd * lg(pd * pd) + 6 * pd * pd
+                      + (0 if pd == 256 else 2 * 5 * N * N * lg(N * N) + 6 * N * N)),
+            "szmap_plus_filter": 2 * 5 * pd * pd * lg(pd * pd) + 2 * 5 * N * N * lg(N * N) + 6 * pd * pd + 6 * N * N,
         }

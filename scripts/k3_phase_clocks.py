@@ -1,7 +1,7 @@
 """Developer tool: SM cycles per phase of the map kernel (K3).
 
 Builds a private copy of the library with -DJX_K3_CLOCKS (build/libjoxsz_b200_clk.so), runs the shipped
-geometry with W walkers and prints the cycles per walker of phases A0 / A1 / B / C / D as seen by thread 0
+geometry with W walkers and prints the cycles per walker of phases A0 / A1 / B / C as seen by thread 0
 of each CTA.  Usage (on a GPU box): python scripts/k3_phase_clocks.py [W]
 """
 import ctypes as C
@@ -57,8 +57,8 @@ if __name__ == "__main__":
     torch.cuda.synchronize()
     lib.jx_debug_k3_clocks(out)
     nfin = int(torch.isfinite(ll).sum()) if hasattr(ll, "sum") else int(np.isfinite(ll).sum())
-    names = ["A0 synth", "A1 rows", "B cols", "C rows", "D filter"]
-    tot = sum(out[i] for i in range(5))
+    names = ["A0 synth", "A1 rows", "B cols", "C rows+store"]
+    tot = sum(out[i] for i in range(4))
     print(f"walkers {W} (finite {nfin}), {n} launches; cycles per evaluated walker (thread 0 of its CTA):")
     for i, nm in enumerate(names):
         print(f"  {nm:10s} {out[i] / (n * W):10.0f}  {100.0 * out[i] / tot:5.1f} %")

@@ -35,10 +35,27 @@ def model_stages(pk, pp):
     S = S * pk.bhat.T[None]                                  # bhat[ky, kx]
     X2 = np.swapaxes(dct_even(S, P, H), 1, 2)                # [W, H(u), Q(kx)]   phase B inverse
     conv = dct_even(X2, P, H)                                # [W, H(u), H(v)]    phase C
-    C1 = conv @ pk.cmat                                      # [W, u, kx]         phase D
-    G = np.einsum("wuk,uk->wk", C1, pk.hf)
-    row = G @ pk.dinv                                        # [W, v]             phase E
+    if P == 256:
+        # shared-memory map kernel + K7: packed triangle u <= v of the convolved map times the filter-row operator
+        iu, iv = np.triu_indices(H)
+        tri = conv[:, iu, iv]                                # [W, H (H + 1) / 2], row-major packed
+        row = tri @ filter_row_operator(pk)                  # [W, v]
+    else:
+        # large-map kernel: dense cosine transform of every row, reduced over ky, then the inverse of the row
+        C1 = conv @ pk.cmat                                  # [W, u, kx]         phase D
+        G = np.einsum("wuk,uk->wk", C1, pk.hf)
+        row = G @ pk.dinv                                    # [W, v]             phase E
     return dict(coef=coef, Z=Z, conv=conv, row=row)
+
+
+def filter_row_operator(pk):
+    """R [H (H + 1) / 2, H] as jx_create builds it for K7 (csrc/jx_api.cu): response of map_out[N//2, N//2 + x] to the
+    convolved-map pixel pair conv_c[u, v] = conv_c[v, u], u <= v row-major."""
+    H = pk.map_ops.H
+    iu, iv = np.triu_indices(H)
+    hf, cmat, dinv = (np.asarray(a, dtype=np.longdouble) for a in (pk.hf, pk.cmat, pk.dinv))
+    F = hf[iu] * cmat[iv] + np.where((iu != iv)[:, None], hf[iv] * cmat[iu], 0.0)      # [(u,v), kx]
+    return np.asarray(F @ dinv, dtype=np.float64)
 
 
 def model_tail(pk, row, tsz, calib):

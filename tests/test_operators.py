@@ -58,6 +58,27 @@ def test_model_pipeline_matches_oracle_stages(golden, cl1226_oracle, packed):
         assert abs(tail["chisq"][0] - st["chisq"]) < 1e-8 * max(1.0, st["chisq"])
 
 
+def test_filter_row_operator_is_the_circular_filter(cl1226_oracle, packed):
+    """K7's constant operator applied to the distinct pixels of a D4- and transpose-symmetric map equals the central
+    half row of real(ifft2(fft2(map) * filtering)) (reference joxsz_funcs.py:466-467, :472)."""
+    from kernel_model import filter_row_operator
+    s = cl1226_oracle
+    H = packed.map_ops.H
+    c = H - 1
+    R = filter_row_operator(packed)
+    assert R.shape == (H * (H + 1) // 2, H)
+    rng = np.random.default_rng(11)
+    q = rng.standard_normal((H, H))
+    q = q + q.T                                                   # conv_c[u, v] = conv_c[v, u]
+    full = np.empty((2 * c + 1, 2 * c + 1))
+    a = np.abs(np.arange(2 * c + 1) - c)
+    full[:] = q[a[:, None], a[None, :]]
+    ref = np.real(np.fft.ifft2(np.fft.fft2(full) * s.filtering))[c, c:]
+    iu, iv = np.triu_indices(H)
+    got = q[iu, iv] @ R
+    assert np.max(np.abs(got - ref)) < 1e-12 * np.max(np.abs(ref))
+
+
 def test_y_operator(golden, cl1226_oracle, packed):
     s = cl1226_oracle
     pp, ps = _pp_and_params(golden, s, [0, 2])
