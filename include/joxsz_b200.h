@@ -105,6 +105,9 @@ typedef struct jx_setup {
     const double*  hf;               /* [H, H]  [u, kx]  w_u sum_ky filt[ky,kx] cos(2 pi ky u / N) */
     const double*  dinv;             /* [H, H]  [kx, v]  w_kx cos(2 pi kx v / N) / N^2 */
     const double*  filt_q;           /* [H, H]  filtering[:H, :H] (full-map tap only) */
+    int32_t nbeam;                   /* B/2 + 1: half-side of the beam image incl. the centre (joxsz_funcs.py:55-77) */
+    const double*  bmix;             /* [nbeam, P/2+1] beam in (y offset j, x frequency kx) * step^2 / P: the map
+                                        kernel convolves along y directly when nbeam <= 28 and H <= 88 */
     /* -- SZ tail (joxsz_funcs.py:469-479) */
     const double*  w_t0;             /* [nt]  h(0) = w_t0 . t_prof */
     int32_t nconv;

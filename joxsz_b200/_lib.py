@@ -37,7 +37,7 @@ class JxSetup(C.Structure):
         ("nr", C.c_int32), ("nt", C.c_int32), ("nmap", C.c_int32), ("nh", C.c_int32),
         ("npad", C.c_int32), ("nseg", C.c_int32),
         ("r_pp", _pd), ("proj_op", _pd), ("y_op", _pd), ("seg", _pi), ("dx", _pd), ("bhat", _pd),
-        ("cmat", _pd), ("hf", _pd), ("dinv", _pd), ("filt_q", _pd),
+        ("cmat", _pd), ("hf", _pd), ("dinv", _pd), ("filt_q", _pd), ("nbeam", C.c_int32), ("bmix", _pd),
         ("w_t0", _pd), ("nconv", C.c_int32), ("conv_T", _pd), ("conv_I", _pd),
         ("nd", C.c_int32), ("g_op", _pd), ("flux", _pd), ("flux_err", _pd),
         ("calc_integ", C.c_int32), ("w_integ", _pd), ("integ_mu", C.c_double), ("integ_sig", C.c_double),

@@ -187,18 +187,25 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     UP(prior_b, s->prior_b, s->ndim);
     UP(r_pp, s->r_pp, s->nr);
     if (!rc) rc = upload_padded(h, &d.proj_op_tap, s->proj_op, d.ncoef, s->nr, d.nrp);
-    if (!rc) {   // production layout: the 4 coefficients of a spline piece adjacent (one 32-byte entry per piece)
+    if (!rc) {   // production layout: two planes of 16-byte entries, row 2 g + p of plane 0 = coefficient p (0, 1) of
+                 // piece g, row 2 nseg + 2 g + (p - 2) = coefficient p (2, 3): see spline_eval (k3_common.cuh)
         std::vector<double> il((size_t)d.ncoef * s->nr);
         for (int p = 0; p < 4; ++p)
             for (int g = 0; g < s->nseg; ++g)
-                memcpy(&il[((size_t)g * 4 + p) * s->nr], s->proj_op + ((size_t)p * s->nseg + g) * s->nr,
-                       sizeof(double) * s->nr);
+                memcpy(&il[((size_t)(p >> 1) * 2 * s->nseg + 2 * g + (p & 1)) * s->nr],
+                       s->proj_op + ((size_t)p * s->nseg + g) * s->nr, sizeof(double) * s->nr);
         rc = upload_padded(h, &d.proj_op, il.data(), d.ncoef, s->nr, d.nrp);
     }
     if (!rc) rc = upload_padded(h, &d.y_op, s->y_op, s->nr, s->nr, d.nrp);
     UP(seg, s->seg, H * H);
     UP(dx, s->dx, H * H);
     UP(bhat, s->bhat, Q * Q);
+    d.nbeam = s->nbeam;
+    if (!rc && s->bmix && s->nbeam >= 1 && s->nbeam <= JX_BMIX_ROWS && Q <= JX_BMIX_PITCH) {
+        std::vector<double> t((size_t)JX_BMIX_ROWS * JX_BMIX_PITCH, 0.0);
+        for (int j = 0; j < s->nbeam; ++j) memcpy(&t[(size_t)j * JX_BMIX_PITCH], s->bmix + (size_t)j * Q, sizeof(double) * Q);
+        rc = upload(h, &d.bmix, t.data(), t.size());
+    }
     UP(hf, s->hf, H * H);
     UP(dinv, s->dinv, H * H);
     UP(filt_q, s->filt_q, H * H);

@@ -17,6 +17,7 @@
 
 constexpr int JX_WARP = 32;
 constexpr int JX_MAX_NDIM = 32;   // theta columns handled by one warp
+constexpr int JX_BMIX_ROWS = 28, JX_BMIX_PITCH = 132;   // device layout of jx_dev::bmix (K3 direct phase B)
 
 // One quarter-plane pixel of the Compton-y map, for the synthesis phase of K3: the spline piece that
 // covers its distance from the centre and the offset from that piece's left knot.  (u, v) and (v, u)
@@ -40,12 +41,14 @@ struct jx_dev {
         ncoef /* 4*nseg */;
     const double* r_pp;
     const double *ln_r_pp, *ln_midpt;   // natural logs of r_pp / midpt_kpc (derived at jx_create)
-    const double* proj_op;   // [ncoef, nrp] zero padded, rows interleaved [seg][4] (production layout)
+    const double* proj_op;   // [ncoef, nrp] zero padded, rows in two planes [c0 c1 per piece][c2 c3 per piece] (production layout)
     const double* proj_op_tap; // [ncoef, nrp] rows [4][seg] as supplied (jx_sz_project's `coef` output)
     const double* y_op;      // [nr, nrp] zero padded
     const int32_t* seg;      // [nh, nh]
     const double* dx;        // [nh, nh]
     const double* bhat;      // [nq, nq]
+    int nbeam;               // beam half-side incl. the centre
+    const double* bmix;      // [28, JX_BMIX_PITCH] beam in (y offset, kx), zero rows beyond nbeam; NULL when nbeam > 28
     const double* cmat_t;    // [nh, nh] transposed on upload: [kx, v]
     const double* hf;        // [nh, nh] [u, kx]
     const double* dinv;      // [nh, nh] [kx, v]

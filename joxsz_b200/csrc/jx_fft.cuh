@@ -113,10 +113,11 @@ JX_HD void fft256_pass1(int t, double (&re)[16], double (&im)[16], const double2
 }
 
 // pass 2 of thread q: afterwards position p holds X[q + 16 rev16(p)]
-JX_HD void fft256_pass2(int q, double (&re)[16], double (&im)[16], const double2* __restrict__ xbuf) {
+JX_HD void fft256_pass2(int q, double (&re)[16], double (&im)[16], const double2* __restrict__ xbuf, bool on = true) {
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
-        double2 v = xbuf[q * JX_XB_PITCH + n1];
+        double2 v = make_double2(0.0, 0.0);
+        if (on) v = xbuf[q * JX_XB_PITCH + n1];
         re[n1] = v.x;
         im[n1] = v.y;
     }
@@ -134,16 +135,21 @@ JX_HD void fft256_pass2(int q, double (&re)[16], double (&im)[16], const double2
 constexpr int JX_XE_ROWS = 9;
 constexpr int JX_XE_ELEMS = JX_XE_ROWS * JX_XB_PITCH;     // double2 elements per 9-thread group
 
-JX_HD void fft256e_pass1(int t, double (&re)[16], double (&im)[16], const double2* __restrict__ tw,
-                         double2* __restrict__ xbuf) {
+// `tw_t` points at this thread's twiddles, w256^(t k2) at tw_t[k2 * TWS]: TWS = 16 with the [k2][t] table of
+// fft256_make_twiddle (tw + t), or a per-lane copy [k2][lane] (TWS = 32) whose quarter-warps read 8 consecutive
+// 16-byte entries -- in the [k2][t] table thread 8 and thread 0 of neighbouring groups share a bank.
+// `on` = false (a lane that only shadows another one) skips the exchange stores.
+template <int TWS>
+JX_HD void fft256e_pass1(int t, double (&re)[16], double (&im)[16], const double2* __restrict__ tw_t,
+                         double2* __restrict__ xbuf, bool on = true) {
     dft16(re, im);
-    const bool mirror = t >= 1 && t <= 7;
+    const bool mirror = on && t >= 1 && t <= 7;
 #pragma unroll
     for (int k2 = 0; k2 < JX_XE_ROWS; ++k2) {
         const int pd = rev16(k2), pm = rev16((16 - k2) & 15);
         double r = re[pd], i = im[pd], mr = re[pm], mi = im[pm];
         if (k2 != 0) {
-            const double2 w = tw[k2 * 16 + t];
+            const double2 w = tw_t[k2 * TWS];
             const double tr = r * w.x - i * w.y;
             i = r * w.y + i * w.x;
             r = tr;
@@ -151,7 +157,7 @@ JX_HD void fft256e_pass1(int t, double (&re)[16], double (&im)[16], const double
             mi = mi * w.x - mr * w.y;
             mr = tm;
         }
-        xbuf[k2 * JX_XB_PITCH + t] = make_double2(r, i);
+        if (on) xbuf[k2 * JX_XB_PITCH + t] = make_double2(r, i);
         if (mirror) xbuf[k2 * JX_XB_PITCH + 16 - t] = make_double2(mr, mi);
     }
 }

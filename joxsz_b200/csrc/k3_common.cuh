@@ -45,11 +45,13 @@ JX_D void dmma884(double& c0, double& c1, double a, double b) {
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// value of the Compton-y spline on piece `s` at offset `t` from its left knot; the 4 coefficients of a
-// piece are adjacent (two 16-byte shared loads), Horner evaluation
-JX_D double spline_eval(const double* __restrict__ c, int s, double t) {
-    const double2 c01 = *reinterpret_cast<const double2*>(c + 4 * s);
-    const double2 c23 = *reinterpret_cast<const double2*>(c + 4 * s + 2);
+// value of the Compton-y spline on piece `s` at offset `t` from its left knot, Horner evaluation.  Coefficient
+// layout: two planes of 16-byte entries, (c0, c1) of piece s at c[2 s] and (c2, c3) at c[2 nseg + 2 s], so that
+// lanes on consecutive pieces read consecutive 16-byte words (a [piece][4] layout would put every load of a
+// quarter-warp on four of the eight 16-byte bank groups)
+JX_D double spline_eval(const double* __restrict__ c, int nseg, int s, double t) {
+    const double2 c01 = *reinterpret_cast<const double2*>(c + 2 * s);
+    const double2 c23 = *reinterpret_cast<const double2*>(c + 2 * nseg + 2 * s);
     return c01.x + t * (c01.y + t * (c23.x + t * c23.y));
 }
 

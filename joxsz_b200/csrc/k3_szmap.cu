@@ -48,6 +48,8 @@ constexpr int K3_NT_A = 512, K3_NT_B = 384, K3_NT_C = 256;
 constexpr int K3_P = 256;
 constexpr int K3_Q = K3_P / 2 + 1;       // 129
 constexpr int K3_XS = 130;               // row pitch of xs (doubles): XS/2 odd -> conflict-free column walks
+// direct phase B: taps per side incl. the centre, rows per thread (4 warp groups), table pitch
+constexpr int K3_NB = 28, K3_UB = 22, K3_BMP = JX_BMIX_PITCH;
 
 struct k3_smem_layout {
     size_t tw, xbuf, xs, coef, mbar, total;
@@ -57,7 +59,7 @@ __host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8, in
     k3_smem_layout L;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~size_t(15); return at; };
-    L.tw = take(256 * sizeof(double2));
+    L.tw = take((size_t)JX_XE_ROWS * 32 * sizeof(double2));
     L.xbuf = take((size_t)(nthreads / 32) * 3 * JX_XE_ELEMS * sizeof(double2));
     L.xs = take((size_t)hp8 * K3_XS * sizeof(double));
     L.coef = take((size_t)2 * d.ncoef * sizeof(double));
@@ -66,7 +68,7 @@ __host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8, in
     return L;
 }
 
-template <int NT>
+template <int NT, bool BDIRECT>
 __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__ k3_args a) {
     extern __shared__ __align__(128) unsigned char k3_raw[];
     const jx_dev& d = a.d;
@@ -80,18 +82,22 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // FFT groups: every sequence the kernel transforms is even, so nine threads carry one length-256 transform
-    // (jx_fft.cuh) and a warp holds three groups; lanes 27..31 shadow the first lanes of group 2 (same loads,
-    // same exchange values) and never store results
+    // (jx_fft.cuh) and a warp holds three groups; lanes 27..31 idle along (no shared-memory access at all: a fifth
+    // lane group in a quarter-warp would collide with the banks of group 2)
     constexpr int NW = NT / 32;
     const bool lane_on = lane < 27;
     const int fg = lane_on ? lane / 9 : 2;
     const int t = lane_on ? lane - 9 * fg : lane - 27;
     const bool t_edge = t == 0 || t == 8;                   // threads whose outputs beyond index 128 repeat earlier ones
     double2* xbuf = xbuf_all + (size_t)(warp * 3 + fg) * JX_XE_ELEMS;
+    const double2* tw_l = tw_s + lane;
     const uint32_t coef_bytes = (uint32_t)(d.ncoef * sizeof(double));
 
     // ---- one-time set-up of the CTA
-    for (int i = tid; i < 256; i += NT) fft256_make_twiddle(i, tw_s[i]);
+    for (int i = tid; i < JX_XE_ROWS * 32; i += NT) {        // per-lane twiddles [k2][lane]: w256^(t(lane) k2)
+        const int l = i & 31, tl = l < 27 ? l % 9 : l - 27;
+        fft256_make_twiddle((i >> 5) * 16 + tl, tw_s[i]);
+    }
     for (int i = tid; i < hp8 * K3_XS; i += NT) xs[i] = 0.0;
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -147,7 +153,7 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
                 for (int k = 0; k < A0_UNROLL; ++k) {
                     const int sg = e[k].z & 0xffff, u = (e[k].z >> 16) & 0xffff, v = e[k].w & 0xffff;
                     if (u != 0xffff) {
-                        const double z = spline_eval(cf, sg, __hiloint2double(e[k].y, e[k].x));
+                        const double z = spline_eval(cf, d.nseg, sg, __hiloint2double(e[k].y, e[k].x));
                         xs[u * K3_XS + v] = z;
                         xs[v * K3_XS + u] = z;
                     }
@@ -167,15 +173,15 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
             for (int j = 0; j < 16; ++j) {
                 const int f = fold256(t + 16 * j);
                 double vr = 0.0, vi = 0.0;
-                if (f < H) {
+                if (lane_on && f < H) {
                     vr = xs[u0 * K3_XS + f];
                     if (has1) vi = xs[u1 * K3_XS + f];
                 }
                 re[j] = vr; im[j] = vi;
             }
-            fft256e_pass1(t, re, im, tw_s, xbuf);
+            fft256e_pass1<32>(t, re, im, tw_l, xbuf, lane_on);
             __syncwarp();
-            fft256_pass2(t, re, im, xbuf);
+            fft256_pass2(t, re, im, xbuf, lane_on);
             __syncwarp();
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
@@ -187,10 +193,65 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
                 }
             }
         }
+        // phase B's beam taps come from L2: start them before waiting for the other warps
+        [[maybe_unused]] double tap[BDIRECT ? K3_NB : 1];
+        [[maybe_unused]] const int bkx = 32 * (warp & 3) + lane;
+        [[maybe_unused]] double ntap[BDIRECT ? 7 : 1];
+        [[maybe_unused]] const int nyq_c = lane >> 3, nyq_u = warp * 6 + (lane & 7);
+        [[maybe_unused]] const bool nyq_on = (lane & 7) < 6 && nyq_u < H;
+        if constexpr (BDIRECT) {
+            static_assert(K3_NB == 28, "the Nyquist column splits 28 taps into 4 chunks of 7");
+#pragma unroll
+            for (int j = 0; j < K3_NB; ++j) tap[j] = __ldg(d.bmix + j * K3_BMP + bkx);
+#pragma unroll
+            for (int i = 0; i < 7; ++i) ntap[i] = __ldg(d.bmix + (7 * nyq_c + i) * K3_BMP + 128);
+        }
         __syncthreads();
         K3_CLK(1);
 
-        // ================= phase B: columns -- cyclic convolution with the beam along y
+        // ================= phase B: beam convolution along y, in place, for every x frequency kx
+        if constexpr (BDIRECT) {
+            // Small beam (at most K3_NB taps each side) and H <= 4 K3_UB: direct convolution in the mixed domain,
+            //   xs[u, kx] <- sum_j bmix[|j|, kx] ext(xs)[u - j, kx],
+            // about the flop count of the two column FFTs but plain FMA streams on 22 independent accumulators: no
+            // exchange, every lane busy, and the 129 columns split evenly (the FFT form needs 65 column pairs on
+            // 48 group slots, i.e. a second, mostly idle round).  Lane = column (conflict-free row segments), the
+            // four warp groups take a quarter of the rows each; the Nyquist column kx = 128 is shared out by rows.
+            static_assert(NT == 512, "direct phase B is laid out for 16 warps");
+            const int kx = bkx, u0 = (warp >> 2) * K3_UB;
+            // Nyquist column kx = 128 first: warp w owns rows 6 w .. 6 w + 5, lane = (row slot, chunk of 7 taps)
+            double nyq = 0.0;
+            if (nyq_on) {
+                const double* col = xs + 128;
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                    const int j = 7 * nyq_c + i, ua = nyq_u - j < 0 ? j - nyq_u : nyq_u - j, ub = nyq_u + j;
+                    const double xa = col[ua * K3_XS], xb = j > 0 && ub < H ? col[ub * K3_XS] : 0.0;   // ua < H always
+                    nyq = fma(ntap[i], xa + xb, nyq);
+                }
+            }
+            nyq += __shfl_xor_sync(0xffffffffu, nyq, 8);
+            nyq += __shfl_xor_sync(0xffffffffu, nyq, 16);
+            double acc[K3_UB];
+#pragma unroll
+            for (int k = 0; k < K3_UB; ++k) acc[k] = 0.0;
+#pragma unroll
+            for (int ii = 0; ii < K3_UB + 2 * (K3_NB - 1); ++ii) {
+                const int up = u0 - (K3_NB - 1) + ii, ua = up < 0 ? -up : up;
+                const double x = ua < H ? xs[ua * K3_XS + kx] : 0.0;
+#pragma unroll
+                for (int k = 0; k < K3_UB; ++k) {
+                    const int j = ii - (K3_NB - 1) - k < 0 ? k + (K3_NB - 1) - ii : ii - (K3_NB - 1) - k;
+                    if (j < K3_NB) acc[k] = fma(tap[j], x, acc[k]);
+                }
+            }
+            __syncthreads();                      // every input has been read: the columns may be overwritten
+#pragma unroll
+            for (int k = 0; k < K3_UB; ++k)
+                if (u0 + k < H) xs[(u0 + k) * K3_XS + kx] = acc[k];
+            if (nyq_on && nyq_c == 0) xs[nyq_u * K3_XS + 128] = nyq;
+        } else {
+        // columns: cyclic convolution through two FFTs per column pair (any beam / map size the kernel admits)
         const int ncpair = (K3_Q + 1) >> 1;
         for (int base = warp * 3; base < ncpair; base += 3 * NW) {
             const bool ok = lane_on && base + fg < ncpair;
@@ -201,12 +262,12 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
             for (int j = 0; j < 16; ++j) {
                 const int f = fold256(t + 16 * j);
                 double2 v = make_double2(0.0, 0.0);
-                if (f < H) v = *reinterpret_cast<const double2*>(xs + f * K3_XS + kx);
+                if (lane_on && f < H) v = *reinterpret_cast<const double2*>(xs + f * K3_XS + kx);
                 re[j] = v.x; im[j] = has1 ? v.y : 0.0;
             }
-            fft256e_pass1(t, re, im, tw_s, xbuf);
+            fft256e_pass1<32>(t, re, im, tw_l, xbuf, lane_on);
             __syncwarp();
-            fft256_pass2(t, re, im, xbuf);
+            fft256_pass2(t, re, im, xbuf, lane_on);
             __syncwarp();
             double re2[16], im2[16];
 #pragma unroll
@@ -216,9 +277,9 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
                 re2[j] = re[rev16(j)] * bh.x;
                 im2[j] = im[rev16(j)] * bh.y;
             }
-            fft256e_pass1(t, re2, im2, tw_s, xbuf);
+            fft256e_pass1<32>(t, re2, im2, tw_l, xbuf, lane_on);
             __syncwarp();
-            fft256_pass2(t, re2, im2, xbuf);
+            fft256_pass2(t, re2, im2, xbuf, lane_on);
             __syncwarp();
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
@@ -228,13 +289,14 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
                     *reinterpret_cast<double2*>(xs + u * K3_XS + kx) = make_double2(re2[p], has1 ? im2[p] : 0.0);
             }
         }
+        }
         __syncthreads();
         K3_CLK(2);
 
         // ================= phase C: rows back to pixel space; conv_c[u, v] for v >= u goes to the packed triangle
         // of this walker (row u starts at u H - u (u - 1) / 2), 72-byte runs per (row, register position)
         double* tri_w = a.tri + (size_t)w * d.ktri;
-        const bool tap = a.convq != nullptr;                  // parity tap: also keep the full quarter plane
+        const bool tapq = a.convq != nullptr;                  // parity tap: also keep the full quarter plane
         for (int base = warp * 3; base < npair; base += 3 * NW) {
             const bool ok = lane_on && base + fg < npair;
             const int u0 = 2 * (base + fg < npair ? base + fg : npair - 1), u1 = u0 + 1;
@@ -242,15 +304,15 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int f = fold256(t + 16 * j);
-                re[j] = xs[u0 * K3_XS + f];
-                im[j] = has1 ? xs[u1 * K3_XS + f] : 0.0;
+                re[j] = lane_on ? xs[u0 * K3_XS + f] : 0.0;
+                im[j] = lane_on && has1 ? xs[u1 * K3_XS + f] : 0.0;
             }
-            fft256e_pass1(t, re, im, tw_s, xbuf);
+            fft256e_pass1<32>(t, re, im, tw_l, xbuf, lane_on);
             __syncwarp();
-            fft256_pass2(t, re, im, xbuf);
+            fft256_pass2(t, re, im, xbuf, lane_on);
             double* tri0 = tri_w + (u0 * H - ((u0 * (u0 - 1)) >> 1) - u0);     // + v
             double* tri1 = tri0 + (H - u0 - 1);                                 // row u1: off(u0) + (H - u0) - u1
-            if (tap) __syncwarp();   // every lane of the warp has read its row pair before the in-place stores
+            if (tapq) __syncwarp();   // every lane of the warp has read its row pair before the in-place stores
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
                 const int n = t + 16 * rev16(p);
@@ -258,7 +320,7 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
                 if (ok && v < H && !(n > 128 && t_edge)) {
                     if (v >= u0) tri0[v] = re[p];
                     if (has1 && v >= u1) tri1[v] = im[p];
-                    if (tap) {
+                    if (tapq) {
                         xs[u0 * K3_XS + v] = re[p];
                         if (has1) xs[u1 * K3_XS + v] = im[p];
                     }
@@ -268,7 +330,7 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
         __syncthreads();        // all reads of xs are done: the next walker's synthesis (or the tap) may proceed
         K3_CLK(3);
 
-        if (tap) {
+        if (tapq) {
             double* cq = a.convq + (size_t)w * H * H;
             for (int i = tid; i < H * H; i += NT) cq[i] = xs[(i / H) * K3_XS + (i % H)];
             // the next iteration's first barrier is after its synthesis writes: order the tap reads before them
@@ -287,7 +349,7 @@ __global__ void k3_tap_y2d_kernel(jx_dev d, const double* coef, int W, double* y
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * N; i += gridDim.x * blockDim.x) {
         int y = i / N, x = i % N;
         int u = y < c ? c - y : y - c, v = x < c ? c - x : x - c;
-        y2d[(size_t)w * N * N + i] = spline_eval(cf, d.seg16[u * H + v], d.dx[u * H + v]);
+        y2d[(size_t)w * N * N + i] = spline_eval(cf, d.nseg, d.seg16[u * H + v], d.dx[u * H + v]);
     }
 }
 
@@ -363,13 +425,24 @@ static int k3_pick_threads(const jx_dev& d) {
     return K3_NT_C;
 }
 
-cudaError_t jx_szmap_configure(const jx_dev& d) {
+// direct y convolution: beam and map small enough for the register tiling, 16 warps; JX_K3_BFFT=1 forces the FFT form
+static bool k3_bdirect(const jx_dev& d, int nt) {
+    if (const char* e = getenv("JX_K3_BFFT")) if (atoi(e)) return false;
+    return nt == K3_NT_A && d.bmix && d.npad == K3_P && d.nbeam <= K3_NB && d.nh <= 4 * K3_UB;
+}
+
+template <class F>
+static auto k3_dispatch(const jx_dev& d, F&& f) {
     const int nt = k3_pick_threads(d);
-    const int bytes = (int)k3_layout(d, d.hp8, nt).total;
-    const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    if (nt == K3_NT_A) return cudaFuncSetAttribute(k3_szmap_kernel<K3_NT_A>, at, bytes);
-    if (nt == K3_NT_B) return cudaFuncSetAttribute(k3_szmap_kernel<K3_NT_B>, at, bytes);
-    return cudaFuncSetAttribute(k3_szmap_kernel<K3_NT_C>, at, bytes);
+    if (nt == K3_NT_A) return k3_bdirect(d, nt) ? f(k3_szmap_kernel<K3_NT_A, true>, nt) : f(k3_szmap_kernel<K3_NT_A, false>, nt);
+    if (nt == K3_NT_B) return f(k3_szmap_kernel<K3_NT_B, false>, nt);
+    return f(k3_szmap_kernel<K3_NT_C, false>, nt);
+}
+
+cudaError_t jx_szmap_configure(const jx_dev& d) {
+    return k3_dispatch(d, [&](auto kern, int nt) {
+        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_layout(d, d.hp8, nt).total);
+    });
 }
 
 size_t jx_szmap_smem_bytes(const jx_dev& d) { return k3_layout(d, d.hp8, k3_pick_threads(d)).total; }
@@ -379,14 +452,11 @@ cudaError_t jx_launch_szmap(const jx_dev& d, const double* coef, const uint32_t*
     if (W <= 0) return cudaSuccess;
     k3_args a;
     a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.g = nullptr; a.tri = tri; a.scratch = nullptr;
-
-    const int nt = k3_pick_threads(d);
-    const size_t bytes = k3_layout(d, d.hp8, nt).total;
     const int grid = W < sm_count ? W : sm_count;
-    if (nt == K3_NT_A) k3_szmap_kernel<K3_NT_A><<<grid, K3_NT_A, bytes, st>>>(a);
-    else if (nt == K3_NT_B) k3_szmap_kernel<K3_NT_B><<<grid, K3_NT_B, bytes, st>>>(a);
-    else k3_szmap_kernel<K3_NT_C><<<grid, K3_NT_C, bytes, st>>>(a);
-    return cudaGetLastError();
+    return k3_dispatch(d, [&](auto kern, int nt) {
+        kern<<<grid, nt, k3_layout(d, d.hp8, nt).total, st>>>(a);
+        return cudaGetLastError();
+    });
 }
 
 cudaError_t jx_launch_tap_y2d(const jx_dev& d, const double* coef, int W, double* y2d, cudaStream_t st) {

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
                 const int4 e = __ldg(tab + i);
                 const int sg = e.z & 0xffff, u = (e.z >> 16) & 0xffff, v = e.w & 0xffff;
                 if (u != 0xffff) {
-                    const double z = spline_eval(cf, sg, __hiloint2double(e.y, e.x));
+                    const double z = spline_eval(cf, d.nseg, sg, __hiloint2double(e.y, e.x));
                     xs[(size_t)u * pitch + v] = z;
                     xs[(size_t)v * pitch + u] = z;
                 }

@@ -228,6 +228,7 @@ class SZMapOperators:
                                        for the map pixel at centred offset (u, v)
     ``nseg``                           number of pieces referenced (pieces 0..nseg-1)
     ``bhat`` [Q,Q]                     ``step^2 / P^2 * sum_{u,v} beam_c[u,v] cos(2pi ky u/P) cos(2pi kx v/P)``
+    ``bmix`` [B//2+1,Q]                ``step^2 / P * sum_v beam_c[j,v] cos(2pi kx v/P)``: beam in (y offset, kx)
     ``cmat`` [H,H]                     ``w_v cos(2 pi kx v / N)`` indexed [v, kx]: row DCT at length N
     ``hf``   [H,H]                     ``w_u sum_ky filt[ky,kx] cos(2 pi ky u / N)`` indexed [u, kx]
     ``dinv`` [H,H]                     ``w_kx cos(2 pi kx v / N) / N^2`` indexed [kx, v]
@@ -280,6 +281,9 @@ class SZMapOperators:
         wb = _fold_weights(b + 1)
         cb = _cos_table(Q, b + 1, P) * wb[None, :]   # [k, u]
         self.bhat = (cb @ bq @ cb.T) * (float(step) ** 2 / float(P) ** 2)
+        # mixed domain (pixel offset j along y, frequency kx along x): the beam convolution along y done directly,
+        # conv[u, kx] = sum_j bmix[|j|, kx] ext(X1)[u - j, kx]; carries step^2 and the 1/P of the x transforms
+        self.bmix = np.ascontiguousarray((bq @ cb.T) * (float(step) ** 2 / float(P)))   # [b+1, Q]
 
         # --- exact length-N circular filter, reduced to the one row that is consumed
         wN = _fold_weights(H)

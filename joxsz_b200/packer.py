@@ -156,6 +156,7 @@ class PackedSetup:
         self.seg = _i32(mo.seg)
         self.dx = _f64(mo.dx)
         self.bhat = _f64(mo.bhat)
+        self.bmix = _f64(mo.bmix)
         self.cmat = _f64(mo.cmat)
         self.hf = _f64(mo.hf)
         self.dinv = _f64(mo.dinv)
@@ -251,6 +252,7 @@ class PackedSetup:
         s.prior_kind, s.prior_a, s.prior_b = pi(self.prior_kind), pd(self.prior_a), pd(self.prior_b)
         s.r_pp, s.proj_op, s.y_op = pd(self.r_pp), pd(self.proj_op), pd(self.y_op)
         s.seg, s.dx, s.bhat = pi(self.seg), pd(self.dx), pd(self.bhat)
+        s.nbeam, s.bmix = int(self.bmix.shape[0]), pd(self.bmix)
         s.cmat, s.hf, s.dinv, s.filt_q = pd(self.cmat), pd(self.hf), pd(self.dinv), pd(self.filt_q)
         s.w_t0, s.conv_T, s.conv_I = pd(self.w_t0), pd(self.conv_T), pd(self.conv_I)
         s.g_op, s.flux, s.flux_err = pd(self.g_op), pd(self.flux), pd(self.flux_err)

@@ -84,7 +84,7 @@ int main() {
             for (int t = 0; t < 9; ++t)
                 for (int j = 0; j < 16; ++j) { int f = fold256(t + 16 * j); re[t][j] = a[f]; im[t][j] = b[f]; }
             for (auto& e : xe) e = make_double2(1e300, 1e300);        // poison: unread entries must not matter
-            for (int t = 0; t < 9; ++t) fft256e_pass1(t, re[t], im[t], tw.data(), xe.data());
+            for (int t = 0; t < 9; ++t) fft256e_pass1<16>(t, re[t], im[t], tw.data() + t, xe.data());
             for (int t = 0; t < 9; ++t) fft256_pass2(t, re[t], im[t], xe.data());
             std::vector<int> seen(129, 0);
             for (int q = 0; q < 9; ++q)

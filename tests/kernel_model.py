@@ -22,7 +22,7 @@ def dct_even(a, P, nout):
     return np.real(np.fft.fft(even_ext(a, P), axis=-1))[..., :nout]
 
 
-def model_stages(pk, pp):
+def model_stages(pk, pp, direct_b=False):
     """pk: PackedSetup, pp [W, nr] -> dict of stage outputs as the kernels define them."""
     mo = pk.map_ops
     W = pp.shape[0]
@@ -31,9 +31,19 @@ def model_stages(pk, pp):
     seg, dx = pk.seg, pk.dx
     Z = coef[:, 0][:, seg] + dx * (coef[:, 1][:, seg] + dx * (coef[:, 2][:, seg] + dx * coef[:, 3][:, seg]))
     X1 = dct_even(Z, P, Q)                                   # [W, H(u), Q(kx)]   phase A
-    S = dct_even(np.swapaxes(X1, 1, 2), P, Q)                # [W, Q(kx), Q(ky)]  phase B forward
-    S = S * pk.bhat.T[None]                                  # bhat[ky, kx]
-    X2 = np.swapaxes(dct_even(S, P, H), 1, 2)                # [W, H(u), Q(kx)]   phase B inverse
+    if direct_b:
+        # phase B as the kernel does it when the beam is small: direct convolution along y in the mixed domain
+        nb = pk.bmix.shape[0]
+        ext = np.zeros((W, H + 2 * (nb - 1), Q))             # rows -(nb-1) .. H+nb-2 of the even extension
+        ext[:, nb - 1:nb - 1 + H] = X1
+        ext[:, :nb - 1] = X1[:, nb - 1:0:-1]
+        X2 = np.zeros_like(X1)
+        for j in range(-(nb - 1), nb):
+            X2 += pk.bmix[abs(j)][None, None, :] * ext[:, nb - 1 - j:nb - 1 - j + H]
+    else:
+        S = dct_even(np.swapaxes(X1, 1, 2), P, Q)            # [W, Q(kx), Q(ky)]  phase B forward
+        S = S * pk.bhat.T[None]                              # bhat[ky, kx]
+        X2 = np.swapaxes(dct_even(S, P, H), 1, 2)            # [W, H(u), Q(kx)]   phase B inverse
     conv = dct_even(X2, P, H)                                # [W, H(u), H(v)]    phase C
     if P == 256:
         # shared-memory map kernel + K7: packed triangle u <= v of the convolved map times the filter-row operator

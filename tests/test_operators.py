@@ -58,6 +58,17 @@ def test_model_pipeline_matches_oracle_stages(golden, cl1226_oracle, packed):
         assert abs(tail["chisq"][0] - st["chisq"]) < 1e-8 * max(1.0, st["chisq"])
 
 
+def test_direct_y_convolution_equals_fft_path(golden, cl1226_oracle, packed):
+    """The mixed-domain beam table `bmix` (direct convolution along y, K3 phase B) gives the same convolved map as the
+    cyclic FFT path with the beam spectrum `bhat`."""
+    pp, _ = _pp_and_params(golden, cl1226_oracle, [0, 3])
+    a = model_stages(packed, pp)
+    b = model_stages(packed, pp, direct_b=True)
+    assert packed.bmix.shape == (28, 129)
+    assert rel_err_max(b["conv"], a["conv"]) < 1e-13
+    assert rel_err_max(b["row"], a["row"]) < 1e-11
+
+
 def test_filter_row_operator_is_the_circular_filter(cl1226_oracle, packed):
     """K7's constant operator applied to the distinct pixels of a D4- and transpose-symmetric map equals the central
     half row of real(ifft2(fft2(map) * filtering)) (reference joxsz_funcs.py:466-467, :472)."""
