@@ -378,6 +378,7 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
         } else if (!jx_filter_supported(d)) {
             rc = fail(h, JX_ERR_INVALID, "filter GEMM: map quarter plane wider than 136 pixels");
         } else {
+            d.k3_direct = jx_szmap_direct_ok(d) ? 1 : 0;
             cudaError_t e = jx_szmap_configure(d);
             if (e == cudaSuccess) e = jx_filter_configure(d);
             if (e != cudaSuccess) rc = cuda_fail(h, e, "configure map / filter kernels");

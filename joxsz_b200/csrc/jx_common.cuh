@@ -48,6 +48,7 @@ struct jx_dev {
     const double* dx;        // [nh, nh]
     const double* bhat;      // [nq, nq]
     int nbeam;               // beam half-side incl. the centre
+    int k3_direct;           // map kernel convolves along y directly (jx_szmap_direct_ok at jx_create)
     const double* bmix;      // [28, JX_BMIX_PITCH] beam in (y offset, kx), zero rows beyond nbeam; NULL when nbeam > 28
     const double* cmat_t;    // [nh, nh] transposed on upload: [kx, v]
     const double* hf;        // [nh, nh] [u, kx]
@@ -148,6 +149,7 @@ cudaError_t jx_launch_tail(const jx_dev& d, const double* theta, const double* r
                            const double* tsz, const uint32_t* flags, const double* prior, const double* xlike,
                            const double* cint, int W, double* bright, double* model, double* chisq, double* ll,
                            double* row_out, cudaStream_t st);
+bool jx_szmap_direct_ok(const jx_dev& d);
 cudaError_t jx_szmap_configure(const jx_dev& d);   // one-time cudaFuncSetAttribute
 cudaError_t jx_launch_tap_y2d(const jx_dev& d, const double* coef, int W, double* y2d, cudaStream_t st);
 cudaError_t jx_launch_tap_expand(const jx_dev& d, const double* convq, int W, double* conv2d, cudaStream_t st);

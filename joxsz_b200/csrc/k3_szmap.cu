@@ -425,16 +425,17 @@ static int k3_pick_threads(const jx_dev& d) {
     return K3_NT_C;
 }
 
-// direct y convolution: beam and map small enough for the register tiling, 16 warps; JX_K3_BFFT=1 forces the FFT form
-static bool k3_bdirect(const jx_dev& d, int nt) {
+// direct y convolution: beam and map small enough for the register tiling, 16 warps; JX_K3_BFFT=1 (read once, at
+// jx_create) forces the FFT form
+bool jx_szmap_direct_ok(const jx_dev& d) {
     if (const char* e = getenv("JX_K3_BFFT")) if (atoi(e)) return false;
-    return nt == K3_NT_A && d.bmix && d.npad == K3_P && d.nbeam <= K3_NB && d.nh <= 4 * K3_UB;
+    return k3_pick_threads(d) == K3_NT_A && d.bmix && d.npad == K3_P && d.nbeam <= K3_NB && d.nh <= 4 * K3_UB;
 }
 
 template <class F>
 static auto k3_dispatch(const jx_dev& d, F&& f) {
     const int nt = k3_pick_threads(d);
-    if (nt == K3_NT_A) return k3_bdirect(d, nt) ? f(k3_szmap_kernel<K3_NT_A, true>, nt) : f(k3_szmap_kernel<K3_NT_A, false>, nt);
+    if (nt == K3_NT_A) return d.k3_direct ? f(k3_szmap_kernel<K3_NT_A, true>, nt) : f(k3_szmap_kernel<K3_NT_A, false>, nt);
     if (nt == K3_NT_B) return f(k3_szmap_kernel<K3_NT_B, false>, nt);
     return f(k3_szmap_kernel<K3_NT_C, false>, nt);
 }

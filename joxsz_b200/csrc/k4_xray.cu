@@ -10,7 +10,8 @@
 //   like   = sum_bands [ sum_j cts_j ln pred_j - sum_j pred_j ]   over bins with cts_j not NaN
 //
 // Lane a owns shell a for the emissivity and annulus a for the projection; the per-walker rate vector
-// goes through shared memory.  Tables (2 x nb x ntab doubles) and projvols are read through the
+// goes through shared memory.  With at most 16 annuli (the shipped layout has 15) a warp carries two walkers,
+// one per half-warp: the kernel is bound by the latency of its dependent table look-ups, not by throughput.  Tables (2 x nb x ntab doubles) and projvols are read through the
 // read-only path and stay L1/L2 resident (every warp reads the same 16 KB).
 #include "jx_common.cuh"
 
@@ -53,13 +54,27 @@ JX_D double np_interp_eval(int lo, double x, double x0, const double* __restrict
     return slope * (x - x0) + f0;
 }
 
+// sum over the lanes of a walker: the whole warp (PER_WARP = 1) or its half-warp (PER_WARP = 2); the xor tree over
+// 16 lanes gives bit-identical sums to the 32-lane tree with zeros in the upper half
+template <int PER_WARP>
+JX_D double k4_sum(double v) {
+#pragma unroll
+    for (int o = 16 / PER_WARP; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int PER_WARP>
 __global__ void __launch_bounds__(K4_WARPS * 32) k4_xray_kernel(const __grid_constant__ k4_args a) {
     extern __shared__ double k4_smem[];
     const jx_dev& d = a.d;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = blockIdx.x * K4_WARPS + warp;
-    if (w >= a.W) return;
-    double* rate_s = k4_smem + (size_t)warp * d.na;
+    constexpr int LANES = 32 / PER_WARP;
+    const int sub = lane / LANES;                                   // which walker of the warp
+    const int w0 = (blockIdx.x * K4_WARPS + warp) * PER_WARP;
+    if (w0 >= a.W) return;                                          // whole warps leave
+    const bool live = w0 + sub < a.W;                               // an odd batch leaves the last half-warp idle
+    const int w = live ? w0 + sub : w0;
+    double* rate_s = k4_smem + (size_t)(warp * PER_WARP + sub) * d.na;
 
     const int zsrc = d.slot_src[JX_ZMET], bsrc = d.slot_src[JX_BACKSCALE];
     const double Z = zsrc < 0 ? d.slot_val[JX_ZMET] : a.theta[(size_t)w * d.ndim + zsrc];
@@ -68,7 +83,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_xray_kernel(const __grid_con
     double like = 0.0;
     bool nonpos = false;
     // one lane per shell/annulus: na <= 32 is enforced by jx_create
-    const int s = lane;                 // shell / annulus index of this lane
+    const int s = lane % LANES;         // shell / annulus index of this lane
     double ne = 0.0, lnT = 0.0;
     if (s < d.na) {
         ne = a.ne_ann[(size_t)w * d.na + s];
@@ -97,17 +112,18 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_xray_kernel(const __grid_con
             for (int k = 0; k < d.na; ++k) proj += __ldg(pv + k) * rate_s[k];
             size_t o = (size_t)b * d.na + s;
             double pred = proj * __ldg(d.srcscale + o) + __ldg(d.bkgterm + o) * backscale;
-            if (a.pred) a.pred[((size_t)w * d.nb + b) * d.na + s] = pred;
+            if (a.pred && live) a.pred[((size_t)w * d.nb + b) * d.na + s] = pred;
             if (!(pred > 0.0)) nonpos = true;
             double c = __ldg(d.cts + o);
             if (c == c) { t1 = c * log(pred); t2 = pred; }
         }
         __syncwarp();
-        double lb = warp_sum(t1) - warp_sum(t2);
+        double lb = k4_sum<PER_WARP>(t1) - k4_sum<PER_WARP>(t2);
         like += isfinite(lb) ? lb : jx_neg_inf();
     }
-    nonpos = __any_sync(0xffffffffu, nonpos);
-    if (lane == 0) {
+    const unsigned np_mask = __ballot_sync(0xffffffffu, nonpos);
+    nonpos = (np_mask & (PER_WARP == 1 ? 0xffffffffu : (0xffffu << (16 * sub)))) != 0u;
+    if (s == 0 && live) {
         if (a.cash) a.cash[w] = nonpos ? jx_neg_inf() : like;
         if (a.flags && nonpos) a.flags[w] |= JX_FLAG_XNONPOS;
     }
@@ -144,8 +160,14 @@ cudaError_t jx_launch_xray(const jx_dev& d, const double* theta, const double* n
                            int W, double* pred, double* cash, uint32_t* flags, cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
     k4_args a{d, theta, ne_ann, tx_ann, W, pred, cash, flags};
-    size_t smem = (size_t)K4_WARPS * d.na * sizeof(double);
-    int blocks = (W + K4_WARPS - 1) / K4_WARPS;
-    k4_xray_kernel<<<blocks, K4_WARPS * 32, smem, st>>>(a);
+    if (d.na <= 16) {
+        const size_t smem = (size_t)K4_WARPS * 2 * d.na * sizeof(double);
+        const int blocks = (W + 2 * K4_WARPS - 1) / (2 * K4_WARPS);
+        k4_xray_kernel<2><<<blocks, K4_WARPS * 32, smem, st>>>(a);
+    } else {
+        const size_t smem = (size_t)K4_WARPS * d.na * sizeof(double);
+        const int blocks = (W + K4_WARPS - 1) / K4_WARPS;
+        k4_xray_kernel<1><<<blocks, K4_WARPS * 32, smem, st>>>(a);
+    }
     return cudaGetLastError();
 }

@@ -201,3 +201,25 @@ def test_getLikelihood_dropin(cl1226_fit, golden):
         assert abs(fit.mylikeFromProfs(profs) - golden["xlike"][0]) < LL_ATOL
     finally:
         fit.updateThawed(saved)
+
+
+def test_fft_form_of_the_beam_convolution(cl1226_fit, golden, engine, monkeypatch):
+    """The map kernel convolves along y directly when the beam is small (the shipped case) and through two column
+    FFTs otherwise; JX_K3_BFFT=1 forces the FFT form so that both stay covered.  Same maps, same likelihood."""
+    from joxsz_b200.batched import BatchedLikelihood
+    monkeypatch.setenv("JX_K3_BFFT", "1")
+    eng = BatchedLikelihood(cl1226_fit, max_walkers=256)
+    try:
+        th = golden["thetas"]
+        ll_fft = eng(th)
+        maps_fft = eng.sz_maps(th[:2], want=("conv_2d",))["conv_2d"]
+    finally:
+        eng.close()
+    monkeypatch.delenv("JX_K3_BFFT")
+    ll = engine(th)
+    ok = np.isfinite(golden["ll"])
+    assert np.array_equal(np.isfinite(ll_fft), ok)
+    assert np.max(np.abs(ll_fft[ok] - golden["ll"][ok])) < LL_ATOL
+    assert np.max(np.abs(ll_fft[ok] - ll[ok])) < 1e-9
+    maps = engine.sz_maps(th[:2], want=("conv_2d",))["conv_2d"]
+    assert rel_err_max(maps_fft, maps) < 1e-12
