@@ -43,6 +43,8 @@ class BatchedLikelihood:
         self._h = handle
         self._pinned_in = None
         self._pinned_out = None
+        self._dev_in = None
+        self._dev_out = None
 
     # ------------------------------------------------------------------ life cycle
     def close(self):
@@ -101,20 +103,49 @@ class BatchedLikelihood:
         _lib.check(rc, self._h)
         return out
 
-    def __call__(self, theta):
-        """numpy/torch [W, ndim] (or [ndim]) -> same kind of array [W] (or a float)."""
-        single = (np.ndim(theta) == 1) if not isinstance(theta, torch.Tensor) else theta.dim() == 1
-        was_torch = isinstance(theta, torch.Tensor)
-        t = self._theta_dev(theta)
-        ll = self.loglike_device(t)
-        if was_torch and theta.is_cuda:
-            return ll[0] if single else ll
-        W = ll.shape[0]
+    #: host batches larger than this are fed to the device in chunks of this many walkers, so that staging chunk
+    #: i+1 in pinned memory and its host->device copy overlap the kernels of chunk i (results do not depend on
+    #: how a batch is split).  Measured on B200: chunks of 16 384 are 4 % slower than one 65 536-walker call (the
+    #: small kernels and the launch count outweigh the hidden 0.7 ms of staging), hence the large value.
+    HOST_CHUNK = 65536
+
+    def _call_host(self, a):
+        """numpy [W, ndim] -> numpy [W]: pinned staging, async H2D, kernels, async D2H, one synchronisation."""
+        W = a.shape[0]
+        if a.shape[1] != self.ndim:
+            raise ValueError(f"theta must be [W, {self.ndim}], got {a.shape}")
+        if W > self.max_walkers:
+            raise ValueError(f"W={W} exceeds max_walkers={self.max_walkers}")
+        if self._pinned_in is None or self._pinned_in.shape[0] < W:
+            self._pinned_in = torch.empty((max(W, 1), self.ndim), dtype=torch.float64).pin_memory()
         if self._pinned_out is None or self._pinned_out.shape[0] < W:
             self._pinned_out = torch.empty(max(W, 1), dtype=torch.float64).pin_memory()
-        self._pinned_out[:W].copy_(ll, non_blocking=True)
+        if self._dev_in is None or self._dev_in.shape[0] < W:
+            self._dev_in = self._new(max(W, 1), self.ndim)
+            self._dev_out = self._new(max(W, 1))
+        src = torch.from_numpy(a)
+        step = self.HOST_CHUNK if W > self.HOST_CHUNK else max(W, 1)
+        for lo in range(0, W, step):
+            hi = min(W, lo + step)
+            self._pinned_in[lo:hi].copy_(src[lo:hi])                       # host memcpy, overlaps the previous chunk
+            self._dev_in[lo:hi].copy_(self._pinned_in[lo:hi], non_blocking=True)
+            self.loglike_device(self._dev_in[lo:hi], out=self._dev_out[lo:hi])
+            self._pinned_out[lo:hi].copy_(self._dev_out[lo:hi], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        res = self._pinned_out[:W].numpy().copy()
+        return self._pinned_out[:W].numpy().copy()
+
+    def __call__(self, theta):
+        """numpy/torch [W, ndim] (or [ndim]) -> same kind of array [W] (or a float)."""
+        was_torch = isinstance(theta, torch.Tensor)
+        single = theta.dim() == 1 if was_torch else np.ndim(theta) == 1
+        if was_torch and theta.is_cuda:
+            ll = self.loglike_device(self._theta_dev(theta))
+            return ll[0] if single else ll
+        a = theta.detach().numpy() if was_torch else np.asarray(theta)
+        a = np.ascontiguousarray(np.atleast_2d(np.asarray(a, dtype=np.float64)))
+        if a.ndim != 2:
+            raise ValueError(f"theta must be [W, {self.ndim}], got {a.shape}")
+        res = self._call_host(a)
         if was_torch:
             res = torch.from_numpy(res)
         return float(res[0]) if single else res

@@ -142,6 +142,10 @@ constexpr int JX_XE_ELEMS = JX_XE_ROWS * JX_XB_PITCH;     // double2 elements pe
 template <int TWS>
 JX_HD void fft256e_pass1(int t, double (&re)[16], double (&im)[16], const double2* __restrict__ tw_t,
                          double2* __restrict__ xbuf, bool on = true) {
+    // the twiddles are loaded before the butterflies so that their shared-memory latency hides behind them
+    double2 w[JX_XE_ROWS];
+#pragma unroll
+    for (int k2 = 1; k2 < JX_XE_ROWS; ++k2) w[k2] = tw_t[k2 * TWS];
     dft16(re, im);
     const bool mirror = on && t >= 1 && t <= 7;
 #pragma unroll
@@ -149,12 +153,11 @@ JX_HD void fft256e_pass1(int t, double (&re)[16], double (&im)[16], const double
         const int pd = rev16(k2), pm = rev16((16 - k2) & 15);
         double r = re[pd], i = im[pd], mr = re[pm], mi = im[pm];
         if (k2 != 0) {
-            const double2 w = tw_t[k2 * TWS];
-            const double tr = r * w.x - i * w.y;
-            i = r * w.y + i * w.x;
+            const double tr = r * w[k2].x - i * w[k2].y;
+            i = r * w[k2].y + i * w[k2].x;
             r = tr;
-            const double tm = mr * w.x + mi * w.y;        // times conj(w)
-            mi = mi * w.x - mr * w.y;
+            const double tm = mr * w[k2].x + mi * w[k2].y;        // times conj(w)
+            mi = mi * w[k2].x - mr * w[k2].y;
             mr = tm;
         }
         if (on) xbuf[k2 * JX_XB_PITCH + t] = make_double2(r, i);

@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
     }
 
     int it = 0;
+    // status bits of the walker one iteration ahead, so that the load is never waited for
+    uint32_t flag_next = (a.flags && w_first < a.W) ? a.flags[w_first] : 0u;
     for (int w = w_first; w < a.W; w += gridDim.x, ++it) {
         const int buf = it & 1;
         const double* cf = coef_s + (size_t)buf * d.ncoef;
@@ -126,7 +128,11 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
                              &mbar[buf ^ 1]);
             }
         }
-        const bool skip = a.flags && a.flags[w] != 0u;
+        const bool skip = flag_next != 0u;
+        {
+            const int wn = w + gridDim.x;
+            flag_next = (a.flags && wn < a.W) ? a.flags[wn] : 0u;
+        }
         mbar_wait(&mbar[buf], (uint32_t)((it >> 1) & 1));
         if (skip) {                         // block-uniform: the tail kernel writes -inf for flagged walkers
             __syncthreads();                // nobody still polls this mbarrier when thread 0 re-arms it
