@@ -156,6 +156,9 @@ def test_properties_at_full_batch(engine):
     perm = np.random.default_rng(0).permutation(W)
     assert np.array_equal(engine(th[perm]), ll[perm])
     assert np.array_equal(engine(th[:1000]), ll[:1000])
+    # ragged batches: a last half-warp without a walker (X-ray kernel), a last GEMM tile with 1 / 127 / 129 rows
+    for n in (1, 127, 129, 999):
+        assert np.array_equal(engine(th[7:7 + n]), ll[7:7 + n]), n
     assert np.array_equal(engine(th), ll)
     # linearity of the SZ chain in P_0 (calibration fixed): bright scales with P_0 at fixed shape... T_SZ
     # also scales, so test the filtered row, which is linear in the pressure profile
