@@ -34,12 +34,25 @@ def fit511():
     return _build(255, 1024)
 
 
+# two more sizes on the shared-memory map kernel (cyclic length 256): a smaller map (H = 71: direct y convolution,
+# filter GEMM with 9 column tiles) and a larger one (H = 101 > 88: the FFT form of the y convolution at 384
+# threads, filter GEMM with 13 column tiles)
+@pytest.fixture(scope="module")
+def fit141():
+    return _build(70, 320)
+
+
+@pytest.fixture(scope="module")
+def fit201():
+    return _build(100, 320)
+
+
 def _draws(fit, n, seed, frac_bad=0.1):
     from joxsz_b200.synthetic import draw_parameters
     return draw_parameters(fit.thawed, n=n, seed=seed, spread=0.03, frac_bad=frac_bad)
 
 
-@pytest.mark.parametrize("which,P", [("fit255", 512), ("fit511", 1024)])
+@pytest.mark.parametrize("which,P", [("fit141", 256), ("fit201", 256), ("fit255", 512), ("fit511", 1024)])
 def test_tables_and_kernel_algorithm_on_cpu(which, P, request):
     """The packed tables + the kernel's sequence of operations (numpy model) reproduce the oracle's filtered row."""
     from joxsz_b200.packer import PackedSetup
@@ -60,7 +73,7 @@ def test_tables_and_kernel_algorithm_on_cpu(which, P, request):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which,nw", [("fit255", 48), ("fit511", 16)])
+@pytest.mark.parametrize("which,nw", [("fit141", 48), ("fit201", 48), ("fit255", 48), ("fit511", 16)])
 def test_large_map_loglike_matches_oracle(which, nw, request):
     from joxsz_b200.batched import BatchedLikelihood
     fit = request.getfixturevalue(which)
