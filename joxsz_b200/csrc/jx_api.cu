@@ -75,13 +75,18 @@ int check_ready(jx_handle* h, const double* theta, int W) {
 void flush_stage_events(jx_handle* h) {
     if (!h->pending) return;
     cudaEventSynchronize(h->ev[JX_NSTAGE]);
-    // execution order: profiles, xray, project, szmap, filter, tail
-    static const int order[JX_NSTAGE] = {JX_ST_PROFILES, JX_ST_XRAY, JX_ST_PROJECT, JX_ST_SZMAP, JX_ST_FILTER, JX_ST_TAIL};
-    for (int i = 0; i < JX_NSTAGE; ++i) {
+    cudaEventSynchronize(h->evx[1]);
+    // events on the caller's stream: start, profiles, (unused), project, szmap, filter, tail; the X-ray kernel runs
+    // on the side stream, concurrently with the projection GEMM, between evx[0] and evx[1]
+    struct span { int stage; cudaEvent_t a, b; };
+    const span spans[JX_NSTAGE] = {{JX_ST_PROFILES, h->ev[0], h->ev[1]}, {JX_ST_XRAY, h->evx[0], h->evx[1]},
+                                   {JX_ST_PROJECT, h->ev[1], h->ev[3]},  {JX_ST_SZMAP, h->ev[3], h->ev[4]},
+                                   {JX_ST_FILTER, h->ev[4], h->ev[5]},   {JX_ST_TAIL, h->ev[5], h->ev[6]}};
+    for (const span& sp : spans) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) {
-            h->stage_ms[order[i]] += ms;
-            h->stage_launches[order[i]] += 1;     // one kernel per stage
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            h->stage_ms[sp.stage] += ms;
+            h->stage_launches[sp.stage] += 1;     // one kernel per stage
         }
     }
     h->pending = false;
@@ -101,8 +106,15 @@ extern "C" void jx_destroy(jx_handle* h) {
     for (int i = 0; i < h->nallocs; ++i) cudaFree(h->allocs[i]);
     if (h->d.ws_convq) cudaFree(h->d.ws_convq);
     if (h->tap_scratch) cudaFree(h->tap_scratch);
-    if (h->ev_ready)
+    if (h->ev_ready) {
         for (auto& e : h->ev) cudaEventDestroy(e);
+        for (auto& e : h->evx) cudaEventDestroy(e);
+    }
+    if (h->side) {
+        cudaStreamDestroy(h->side);
+        cudaEventDestroy(h->ev_fork);
+        cudaEventDestroy(h->ev_join);
+    }
     delete h;
 }
 
@@ -162,6 +174,7 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     h->profiling = 0;
     h->ev_ready = false;
     h->pending = false;
+    h->side = nullptr;
     memset(h->stage_ms, 0, sizeof h->stage_ms);
     memset(h->stage_launches, 0, sizeof h->stage_launches);
     jx_dev& d = h->d;
@@ -393,6 +406,12 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
             if (!rc) rc = dev_alloc(h, &d.ws_scratch, (size_t)h->sm_count * d.hp8 * d.xs_pitch);
         }
     }
+    if (!rc) {
+        cudaError_t e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "side stream");
+    }
     if (rc) {
         g_create_error = h->err;
         jx_destroy(h);
@@ -438,6 +457,7 @@ extern "C" int jx_loglike(jx_handle* h, const double* theta, int32_t W, double* 
     if (prof) {
         if (!h->ev_ready) {
             for (auto& e : h->ev) JX_CUDA(h, cudaEventCreate(&e));
+            for (auto& e : h->evx) JX_CUDA(h, cudaEventCreate(&e));
             h->ev_ready = true;
         }
         flush_stage_events(h);
@@ -446,14 +466,23 @@ extern "C" int jx_loglike(jx_handle* h, const double* theta, int32_t W, double* 
     JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, d.ws_tsz, d.ws_ne, d.ws_tx, d.ws_flags, d.ws_prior,
                                   d.ws_integ, st));
     if (prof) JX_CUDA(h, cudaEventRecord(h->ev[1], st));
-    JX_CUDA(h, jx_launch_xray(d, theta, d.ws_ne, d.ws_tx, W, nullptr, d.ws_xlike, d.ws_flags, st));
-    if (prof) JX_CUDA(h, cudaEventRecord(h->ev[2], st));
+    // The X-ray kernel (latency bound, a few registers) only depends on the profiles: it runs on the handle's side
+    // stream and shares the SMs with the projection GEMM.  It may set the "profile not > 0" bit of a walker while
+    // the map kernel reads the status word to decide whether to skip that walker: either way the tail kernel,
+    // after the join, writes -inf for it.
+    JX_CUDA(h, cudaEventRecord(h->ev_fork, st));
+    JX_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    if (prof) JX_CUDA(h, cudaEventRecord(h->evx[0], h->side));
+    JX_CUDA(h, jx_launch_xray(d, theta, d.ws_ne, d.ws_tx, W, nullptr, d.ws_xlike, d.ws_flags, h->side));
+    if (prof) JX_CUDA(h, cudaEventRecord(h->evx[1], h->side));
+    JX_CUDA(h, cudaEventRecord(h->ev_join, h->side));
     JX_CUDA(h, jx_launch_project(d, d.ws_pp, W, d.proj_op, d.ncoef, d.ws_coef, st));
     if (prof) JX_CUDA(h, cudaEventRecord(h->ev[3], st));
     const double* row = nullptr;
     int ld_row = 0, nparts = 1;
     JX_CUDA(h, launch_map_filter(h, d.ws_coef, d.ws_flags, W, nullptr, &row, &ld_row, &nparts, prof ? h->ev[4] : nullptr, st));
     if (prof) JX_CUDA(h, cudaEventRecord(h->ev[5], st));
+    JX_CUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
     JX_CUDA(h, jx_launch_tail(d, theta, row, ld_row, nparts, d.ws_tsz, d.ws_flags, d.ws_prior, d.ws_xlike, d.ws_integ, W,
                               nullptr, nullptr, nullptr, ll, nullptr, st));
     if (prof) {

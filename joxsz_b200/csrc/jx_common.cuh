@@ -112,11 +112,15 @@ struct jx_handle {
     size_t tap_scratch_walkers;
     // profiling
     int profiling;
-    cudaEvent_t ev[JX_NSTAGE + 1];
+    cudaEvent_t ev[JX_NSTAGE + 1];   // ev[0..6] on the caller's stream; the X-ray stage is bracketed by evx[0..1] on the side stream
+    cudaEvent_t evx[2];
     bool ev_ready;
     double stage_ms[JX_NSTAGE];
     int64_t stage_launches[JX_NSTAGE];
     bool pending;            // events recorded but not yet accumulated
+    // the X-ray kernel only depends on the profiles: it runs on a side stream next to the projection GEMM
+    cudaStream_t side;
+    cudaEvent_t ev_fork, ev_join;
     int pending_launches[JX_NSTAGE];
 };
 
