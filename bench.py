@@ -326,6 +326,9 @@ def run_gpu_arm(args):
             tr = json.load(open(os.path.join(ROOT, "profiles", "k3_ncu_traffic.json")))
             roof["traffic"] = tr["dram_bytes_per_launch"] * (k3_walkers / tr["walkers_per_launch"])
             roof["traffic_source"] = tr.get("source")
+            # what the kernel is actually bound by, from the same ncu capture (pipe-busy fractions of the SMs)
+            roof["executed"] = {k: tr[k] for k in ("fp64_pipe_busy_frac", "shared_pipe_busy_frac",
+                                                   "issue_slots_busy_frac") if k in tr}
         except Exception:
             pass
         # every stage against the roofline north_star names for it: HBM for profiles / map / reduction,
