@@ -20,6 +20,7 @@
 // The per-walker inputs (spline coefficients) arrive by TMA bulk copy (cp.async.bulk + mbarrier),
 // double buffered against the previous walker's compute.
 #include "k3_common.cuh"
+#include "jx_tmem.cuh"
 #include <stdlib.h>
 
 // Developer instrumentation (scripts/k3_phase_clocks.py builds a private copy of the library with
@@ -52,7 +53,7 @@ constexpr int K3_XS = 130;               // row pitch of xs (doubles): XS/2 odd 
 constexpr int K3_NB = 28, K3_UB = 22, K3_BMP = JX_BMIX_PITCH;
 
 struct k3_smem_layout {
-    size_t tw, xbuf, xs, coef, mbar, total;
+    size_t tw, xbuf, xs, coef, mbar, tmem, total;
 };
 
 __host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8, int nthreads) {
@@ -64,6 +65,7 @@ __host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8, in
     L.xs = take((size_t)hp8 * K3_XS * sizeof(double));
     L.coef = take((size_t)2 * d.ncoef * sizeof(double));
     L.mbar = take(2 * sizeof(uint64_t));
+    L.tmem = take(sizeof(uint32_t));
     L.total = o;
     return L;
 }
@@ -104,7 +106,48 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    // Direct variant: the per-thread constants of the walker loop -- this thread's 8 entries of the synthesis table,
+    // its 28 beam taps and its 7 Nyquist taps, 204 bytes -- live in tensor memory (unused otherwise: no tcgen05.mma
+    // in an FP64 kernel), written once here and read back with tcgen05.ld every walker instead of 36 loads from L2.
+    // Thread i of warp w owns TMEM lane 32 (w % 4) + i; the four warps of a lane quarter take 128 columns each.
+    [[maybe_unused]] uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k3_raw + L.tmem);
+    [[maybe_unused]] uint32_t tm_base = 0, tm_mine = 0;
+    if constexpr (BDIRECT) {
+        if (warp == 0) tmem_alloc(tmem_slot, 512);
+        tmem_fence_before_sync();
+    }
     __syncthreads();
+    if constexpr (BDIRECT) {
+        tmem_fence_after_sync();
+        tm_base = *tmem_slot;
+        tm_mine = tm_base + ((uint32_t)(32 * (warp & 3)) << 16) + 128u * (uint32_t)(warp >> 2);
+        uint32_t r[64];
+        const int4* tab = reinterpret_cast<const int4*>(d.synth);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = k * NT + tid;
+            const int4 e = i < d.nsynth ? __ldg(tab + i) : make_int4(0, 0, 0xffff0000, 0);
+            r[4 * k] = (uint32_t)e.x; r[4 * k + 1] = (uint32_t)e.y; r[4 * k + 2] = (uint32_t)e.z; r[4 * k + 3] = (uint32_t)e.w;
+        }
+        tmem_st32(tm_mine, reinterpret_cast<uint32_t(&)[32]>(r));
+        tmem_wait_st();
+        const int kxc = 32 * (warp & 3) + lane, nc = lane >> 3;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {           // taps 0..27 of column kxc, then Nyquist taps 7 nc .. 7 nc + 3
+            const double v = j < K3_NB ? __ldg(d.bmix + j * K3_BMP + kxc) : __ldg(d.bmix + (7 * nc + j - K3_NB) * K3_BMP + 128);
+            r[2 * j] = (uint32_t)__double2loint(v); r[2 * j + 1] = (uint32_t)__double2hiint(v);
+        }
+        tmem_st64(tm_mine + 32, r);
+        tmem_wait_st();
+        uint32_t q[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {            // Nyquist taps 7 nc + 4 .. 7 nc + 6 (+ one pad)
+            const double v = j < 3 ? __ldg(d.bmix + (7 * nc + 4 + j) * K3_BMP + 128) : 0.0;
+            q[2 * j] = (uint32_t)__double2loint(v); q[2 * j + 1] = (uint32_t)__double2hiint(v);
+        }
+        tmem_st8(tm_mine + 96, q);
+        tmem_wait_st();
+    }
 
     const int w_first = blockIdx.x;
     if (tid == 0 && w_first < a.W) {
@@ -150,10 +193,19 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
             const int4* tab = reinterpret_cast<const int4*>(d.synth);
             for (int base = 0; base < d.nsynth; base += A0_UNROLL * NT) {
                 int4 e[A0_UNROLL];
+                if constexpr (BDIRECT) {         // nsynth <= 8 NT: one pass, entries from tensor memory
+                    static_assert(A0_UNROLL == 8, "TMEM holds 8 table entries per thread");
+                    uint32_t r[32];
+                    tmem_ld32(tm_mine, r);
+                    tmem_wait_ld();
 #pragma unroll
-                for (int k = 0; k < A0_UNROLL; ++k) {
-                    const int i = base + k * NT + tid;
-                    e[k] = i < d.nsynth ? __ldg(tab + i) : make_int4(0, 0, 0xffff0000, 0);
+                    for (int k = 0; k < A0_UNROLL; ++k) e[k] = make_int4((int)r[4 * k], (int)r[4 * k + 1], (int)r[4 * k + 2], (int)r[4 * k + 3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < A0_UNROLL; ++k) {
+                        const int i = base + k * NT + tid;
+                        e[k] = i < d.nsynth ? __ldg(tab + i) : make_int4(0, 0, 0xffff0000, 0);
+                    }
                 }
 #pragma unroll
                 for (int k = 0; k < A0_UNROLL; ++k) {
@@ -199,19 +251,12 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
                 }
             }
         }
-        // phase B's beam taps come from L2: start them before waiting for the other warps
         [[maybe_unused]] double tap[BDIRECT ? K3_NB : 1];
         [[maybe_unused]] const int bkx = 32 * (warp & 3) + lane;
         [[maybe_unused]] double ntap[BDIRECT ? 7 : 1];
         [[maybe_unused]] const int nyq_c = lane >> 3, nyq_u = warp * 6 + (lane & 7);
         [[maybe_unused]] const bool nyq_on = (lane & 7) < 6 && nyq_u < H;
-        if constexpr (BDIRECT) {
-            static_assert(K3_NB == 28, "the Nyquist column splits 28 taps into 4 chunks of 7");
-#pragma unroll
-            for (int j = 0; j < K3_NB; ++j) tap[j] = __ldg(d.bmix + j * K3_BMP + bkx);
-#pragma unroll
-            for (int i = 0; i < 7; ++i) ntap[i] = __ldg(d.bmix + (7 * nyq_c + i) * K3_BMP + 128);
-        }
+        static_assert(K3_NB == 28, "the Nyquist column splits 28 taps into 4 chunks of 7");
         __syncthreads();
         K3_CLK(1);
 
@@ -225,6 +270,18 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
             // four warp groups take a quarter of the rows each; the Nyquist column kx = 128 is shared out by rows.
             static_assert(NT == 512, "direct phase B is laid out for 16 warps");
             const int kx = bkx, u0 = (warp >> 2) * K3_UB;
+            {   // this thread's taps, from tensor memory
+                uint32_t r[64], q[8];
+                tmem_ld64(tm_mine + 32, r);
+                tmem_ld8(tm_mine + 96, q);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < K3_NB; ++j) tap[j] = __hiloint2double((int)r[2 * j + 1], (int)r[2 * j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ntap[j] = __hiloint2double((int)r[2 * (K3_NB + j) + 1], (int)r[2 * (K3_NB + j)]);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) ntap[4 + j] = __hiloint2double((int)q[2 * j + 1], (int)q[2 * j]);
+            }
             // Nyquist column kx = 128 first: warp w owns rows 6 w .. 6 w + 5, lane = (row slot, chunk of 7 taps)
             double nyq = 0.0;
             if (nyq_on) {
@@ -343,6 +400,11 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
             __syncthreads();
         }
     }
+    if constexpr (BDIRECT) {
+        tmem_fence_before_sync();
+        __syncthreads();
+        if (warp == 0) tmem_dealloc(tm_base, 512);
+    }
 }
 
 // ---- parity taps (not on the production path) -------------------------------------------------
@@ -435,7 +497,8 @@ static int k3_pick_threads(const jx_dev& d) {
 // jx_create) forces the FFT form
 bool jx_szmap_direct_ok(const jx_dev& d) {
     if (const char* e = getenv("JX_K3_BFFT")) if (atoi(e)) return false;
-    return k3_pick_threads(d) == K3_NT_A && d.bmix && d.npad == K3_P && d.nbeam <= K3_NB && d.nh <= 4 * K3_UB;
+    return k3_pick_threads(d) == K3_NT_A && d.bmix && d.npad == K3_P && d.nbeam <= K3_NB && d.nh <= 4 * K3_UB &&
+           d.nsynth <= 8 * K3_NT_A;
 }
 
 template <class F>
