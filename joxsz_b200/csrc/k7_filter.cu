@@ -19,7 +19,8 @@
 // FP64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA): the 1e-6 absolute bar on the log-likelihood needs double
 // operands and accumulation, and tcgen05 has no f64 kind.
 //
-// Tiling: CTA = 128 walkers x all 8 NT outputs, 8 warps, warp tile 16 x 8 NT (2 x NT DMMA tiles), K in chunks
+// Tiling: CTA = 128 walkers x all 8 NT outputs, 16 warps, warp tile 8 x 8 NT (NT DMMA tiles; four warps per
+// scheduler keep the FP64 tensor pipe fed across the per-chunk barrier), K in chunks
 // of 32 through a 3-stage cp.async ring (rows padded to 36 doubles: both fragment loads take the minimum two
 // wavefronts).  K is additionally split into contiguous parts of JX_FILTER_CPP chunks (grid.x) so that walker tiles
 // x parts fills the SMs evenly; part p writes its partial sums to C + p * M * ldc and the tail kernel
@@ -28,7 +29,11 @@
 
 namespace {
 
-constexpr int K7_BM = 128, K7_BK = 32, K7_LDS = K7_BK + 4, K7_STAGES = 3, K7_THREADS = 256;
+constexpr int K7_BM = 128, K7_BK = 32, K7_LDS = K7_BK + 4, K7_STAGES = 3;
+#ifndef K7_WARPS
+#define K7_WARPS 16         // 16 warps x (8 x 8 NT) or 8 warps x (16 x 8 NT)
+#endif
+constexpr int K7_THREADS = 32 * K7_WARPS, K7_MT = K7_BM / (8 * K7_WARPS);   // DMMA row tiles per warp
 
 JX_D void k7_cp16(void* smem, const void* gmem, bool valid) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -81,9 +86,9 @@ k7_filter_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B
         }
     };
 
-    double acc[2][NT][2];
+    double acc[K7_MT][NT][2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < K7_MT; ++i)
 #pragma unroll
         for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
@@ -98,19 +103,19 @@ k7_filter_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B
         const int next = chunk + K7_STAGES - 1;          // reuses the slot consumed in the previous iteration
         if (next < nchunks) load_stage(next % K7_STAGES, next);
         k7_commit();
-        const double* as = As + ((size_t)(chunk % K7_STAGES) * K7_BM + warp * 16 + frow) * K7_LDS + fk;
+        const double* as = As + ((size_t)(chunk % K7_STAGES) * K7_BM + warp * (8 * K7_MT) + frow) * K7_LDS + fk;
         const double* bs = Bs + ((size_t)(chunk % K7_STAGES) * BN + frow) * K7_LDS + fk;
 #pragma unroll
         for (int kk = 0; kk < K7_BK; kk += 4) {
-            double bf[NT];
-            const double a0 = as[kk], a1 = as[(size_t)8 * K7_LDS + kk];
+            double bf[NT], af[K7_MT];
+#pragma unroll
+            for (int i = 0; i < K7_MT; ++i) af[i] = as[(size_t)i * 8 * K7_LDS + kk];
 #pragma unroll
             for (int j = 0; j < NT; ++j) bf[j] = bs[(size_t)j * 8 * K7_LDS + kk];
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                k7_dmma(acc[0][j][0], acc[0][j][1], a0, bf[j]);
-                k7_dmma(acc[1][j][0], acc[1][j][1], a1, bf[j]);
-            }
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int i = 0; i < K7_MT; ++i) k7_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
     }
     k7_wait<0>();
@@ -118,8 +123,8 @@ k7_filter_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B
     // lane owns C[row = lane / 4][col = 2 (lane % 4) + {0, 1}] of each 8 x 8 tile
     double* Cp = C + (size_t)part * M * BN;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int m = m0 + warp * 16 + i * 8 + frow;
+    for (int i = 0; i < K7_MT; ++i) {
+        const int m = m0 + warp * (8 * K7_MT) + i * 8 + frow;
         if (m >= M) continue;
 #pragma unroll
         for (int j = 0; j < NT; ++j)
