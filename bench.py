@@ -344,7 +344,9 @@ def run_gpu_arm(args):
         both_s = (stage_ms["szmap"] + stage_ms.get("filter", 0.0)) * 1e-3
         both_gbs = alg["szmap"] * nw / both_s / 1e9 if both_s > 0 else None
         stage_roof = {"profiles": hbm("profiles", "profiles"), "szmap": hbm("szmap", "szmap"),
-                      "xray": hbm("xray", "xray"), "tail": hbm("tail", "tail"),
+                      "xray": dict(hbm("xray", "xray"), note="side stream: elapsed time overlaps the project / szmap stages "
+                                   "(0.105 ms per 32768 walkers when run alone)"),
+                      "tail": hbm("tail", "tail"),
                       # the transfer-function filter is a GEMM over the walkers (K7) when the cyclic length is 256
                       "filter": {"bound": "tensor(fp64 dmma)", "alg_flops_per_walker": flops["filter"],
                                  "ms": stage_ms.get("filter"), "achieved_tflops": filt_tf,

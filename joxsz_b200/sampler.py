@@ -182,7 +182,16 @@ class EnsembleSampler:
         self._packed = torch.zeros((per, nd + 2), dtype=f64, device=dev)
         self._packed_all = self._packed if self.world == 1 else torch.zeros((per * self.world, nd + 2), dtype=f64,
                                                                             device=dev)
-        self._perm = torch.zeros((W,), dtype=torch.int32, device=dev)
+        # the colouring permutation of iteration i depends on (seed, i) only: two buffers, the one of the next
+        # iteration is produced on a side stream while this iteration's kernels run (CUDA ops only)
+        self._perm2 = [torch.zeros((W,), dtype=torch.int32, device=dev) for _ in range(2)]
+        self._perm_iter = [None, None]
+        self._perm = self._perm2[0]
+        self._side = self._perm_ready = self._step_done = None
+        if dev.type == "cuda" and isinstance(self.ops, CudaStretchOps):
+            self._side = torch.cuda.Stream(device=dev)
+            self._perm_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._step_done = torch.cuda.Event()
         self._steps_done = 0
 
     def _all_gather(self, out, inp):
@@ -234,8 +243,23 @@ class EnsembleSampler:
         """One stretch-move iteration: two half-steps, every walker proposed and evaluated once."""
         W = self.nwalkers
         it = self.iteration
-        self.ops.permutation(self._perm, self.seed, it)
+        cur = it & 1
+        self._perm = self._perm2[cur]
+        if self._perm_iter[cur] != it:               # first step (or a jump of the counter): produce it in line
+            self.ops.permutation(self._perm, self.seed, it)
+            self._perm_iter[cur] = it
+        elif self._side is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._perm_ready[cur])
         self.aux_launches += getattr(self.ops, "launches_per_permutation", 0)
+        if self._side is not None:
+            # next iteration's permutation on the side stream; its buffer was last read by the previous step
+            nxt = cur ^ 1
+            self._side.wait_event(self._step_done) if self._steps_done else self._side.wait_stream(
+                torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self._side):
+                self.ops.permutation(self._perm2[nxt], self.seed, it + 1)
+                self._perm_ready[nxt].record(self._side)
+            self._perm_iter[nxt] = it + 1
         for split in (0, 1):
             ns = (W - split + 1) // 2
             per, first, count = shard_bounds(ns, self.world, self.rank)
@@ -258,6 +282,8 @@ class EnsembleSampler:
                 pa = self._packed
             self.ops.scatter(self._coords, self._lp, self._naccept, self._perm, split, pa, ns)
             self.aux_launches += self.ops.launches_per_half_step
+        if self._side is not None:
+            self._step_done.record(torch.cuda.current_stream(self.device))
         self.iteration += 1
         self._steps_done += 1
 
