@@ -139,13 +139,9 @@ constexpr int JX_XE_ELEMS = JX_XE_ROWS * JX_XB_PITCH;     // double2 elements pe
 // fft256_make_twiddle (tw + t), or a per-lane copy [k2][lane] (TWS = 32) whose quarter-warps read 8 consecutive
 // 16-byte entries -- in the [k2][t] table thread 8 and thread 0 of neighbouring groups share a bank.
 // `on` = false (a lane that only shadows another one) skips the exchange stores.
-template <int TWS>
-JX_HD void fft256e_pass1(int t, double (&re)[16], double (&im)[16], const double2* __restrict__ tw_t,
-                         double2* __restrict__ xbuf, bool on = true) {
-    // the twiddles are loaded before the butterflies so that their shared-memory latency hides behind them
-    double2 w[JX_XE_ROWS];
-#pragma unroll
-    for (int k2 = 1; k2 < JX_XE_ROWS; ++k2) w[k2] = tw_t[k2 * TWS];
+// twiddles already in registers: w[k2] = w256^(t k2), k2 = 1..8 (w[0] unused)
+JX_HD void fft256e_pass1_w(int t, double (&re)[16], double (&im)[16], const double2 (&w)[JX_XE_ROWS],
+                           double2* __restrict__ xbuf, bool on = true) {
     dft16(re, im);
     const bool mirror = on && t >= 1 && t <= 7;
 #pragma unroll
@@ -163,6 +159,16 @@ JX_HD void fft256e_pass1(int t, double (&re)[16], double (&im)[16], const double
         if (on) xbuf[k2 * JX_XB_PITCH + t] = make_double2(r, i);
         if (mirror) xbuf[k2 * JX_XB_PITCH + 16 - t] = make_double2(mr, mi);
     }
+}
+template <int TWS>
+JX_HD void fft256e_pass1(int t, double (&re)[16], double (&im)[16], const double2* __restrict__ tw_t,
+                         double2* __restrict__ xbuf, bool on = true) {
+    // the twiddles are loaded before the butterflies so that their shared-memory latency hides behind them
+    double2 w[JX_XE_ROWS];
+    w[0] = make_double2(1.0, 0.0);
+#pragma unroll
+    for (int k2 = 1; k2 < JX_XE_ROWS; ++k2) w[k2] = tw_t[k2 * TWS];
+    fft256e_pass1_w(t, re, im, w, xbuf, on);
 }
 // pass 2 of thread q = 0..8 is fft256_pass2 (it reads exchange row q only)
 

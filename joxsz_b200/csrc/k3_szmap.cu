@@ -53,7 +53,7 @@ constexpr int K3_XS = 130;               // row pitch of xs (doubles): XS/2 odd 
 constexpr int K3_NB = 28, K3_UB = 22, K3_BMP = JX_BMIX_PITCH;
 
 struct k3_smem_layout {
-    size_t tw, xbuf, xs, coef, mbar, tmem, total;
+    size_t tw, xbuf, xs, coef, nyqt, mbar, tmem, total;
 };
 
 __host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8, int nthreads) {
@@ -64,6 +64,7 @@ __host__ __device__ inline k3_smem_layout k3_layout(const jx_dev& d, int hp8, in
     L.xbuf = take((size_t)(nthreads / 32) * 3 * JX_XE_ELEMS * sizeof(double2));
     L.xs = take((size_t)hp8 * K3_XS * sizeof(double));
     L.coef = take((size_t)2 * d.ncoef * sizeof(double));
+    L.nyqt = take(K3_NB * sizeof(double));             // taps of the Nyquist column (direct phase B)
     L.mbar = take(2 * sizeof(uint64_t));
     L.tmem = take(sizeof(uint32_t));
     L.total = o;
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
     double2* xbuf_all = reinterpret_cast<double2*>(k3_raw + L.xbuf);
     double* xs = reinterpret_cast<double*>(k3_raw + L.xs);
     double* coef_s = reinterpret_cast<double*>(k3_raw + L.coef);
+    [[maybe_unused]] double* nyqt = reinterpret_cast<double*>(k3_raw + L.nyqt);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(k3_raw + L.mbar);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -106,9 +108,10 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    // Direct variant: the per-thread constants of the walker loop -- this thread's 8 entries of the synthesis table,
-    // its 28 beam taps and its 7 Nyquist taps, 204 bytes -- live in tensor memory (unused otherwise: no tcgen05.mma
-    // in an FP64 kernel), written once here and read back with tcgen05.ld every walker instead of 36 loads from L2.
+    // Direct variant: the per-thread constants of the walker loop -- this thread's 8 entries of the synthesis table
+    // (columns 0..31 of its slot), its 28 beam taps (32..87) and its 8 FFT twiddles (96..127) -- live in tensor
+    // memory (unused otherwise: no tcgen05.mma in an FP64 kernel), written once here and read back with tcgen05.ld
+    // every walker instead of 36 loads from L2 and 32 from shared memory.
     // Thread i of warp w owns TMEM lane 32 (w % 4) + i; the four warps of a lane quarter take 128 columns each.
     [[maybe_unused]] uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k3_raw + L.tmem);
     [[maybe_unused]] uint32_t tm_base = 0, tm_mine = 0;
@@ -131,22 +134,25 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
         }
         tmem_st32(tm_mine, reinterpret_cast<uint32_t(&)[32]>(r));
         tmem_wait_st();
-        const int kxc = 32 * (warp & 3) + lane, nc = lane >> 3;
+        const int kxc = 32 * (warp & 3) + lane;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {           // taps 0..27 of column kxc, then Nyquist taps 7 nc .. 7 nc + 3
-            const double v = j < K3_NB ? __ldg(d.bmix + j * K3_BMP + kxc) : __ldg(d.bmix + (7 * nc + j - K3_NB) * K3_BMP + 128);
+        for (int j = 0; j < 32; ++j) {           // taps 0..27 of column kxc (+ 4 pads)
+            const double v = j < K3_NB ? __ldg(d.bmix + j * K3_BMP + kxc) : 0.0;
             r[2 * j] = (uint32_t)__double2loint(v); r[2 * j + 1] = (uint32_t)__double2hiint(v);
         }
         tmem_st64(tm_mine + 32, r);
         tmem_wait_st();
-        uint32_t q[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {            // Nyquist taps 7 nc + 4 .. 7 nc + 6 (+ one pad)
-            const double v = j < 3 ? __ldg(d.bmix + (7 * nc + 4 + j) * K3_BMP + 128) : 0.0;
-            q[2 * j] = (uint32_t)__double2loint(v); q[2 * j + 1] = (uint32_t)__double2hiint(v);
+        for (int k2 = 1; k2 < JX_XE_ROWS; ++k2) {            // w256^(t k2), k2 = 1..8
+            double2 tw;
+            fft256_make_twiddle(k2 * 16 + t, tw);
+            r[4 * (k2 - 1)] = (uint32_t)__double2loint(tw.x); r[4 * (k2 - 1) + 1] = (uint32_t)__double2hiint(tw.x);
+            r[4 * (k2 - 1) + 2] = (uint32_t)__double2loint(tw.y); r[4 * (k2 - 1) + 3] = (uint32_t)__double2hiint(tw.y);
         }
-        tmem_st8(tm_mine + 96, q);
+        tmem_st32(tm_mine + 96, reinterpret_cast<uint32_t(&)[32]>(r));
         tmem_wait_st();
+        if (tid < K3_NB) nyqt[tid] = __ldg(d.bmix + tid * K3_BMP + 128);
+        __syncthreads();
     }
 
     const int w_first = blockIdx.x;
@@ -221,9 +227,31 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
         __syncthreads();
         K3_CLK(0);
 
+        // pass 1 of a row transform; the direct variant takes its twiddles from tensor memory (issued by tw_fetch
+        // before the row loads, so that the two latencies overlap) instead of eight 16-byte shared-memory loads
+        [[maybe_unused]] uint32_t twr[BDIRECT ? 32 : 1];
+        auto tw_fetch = [&]() {
+            if constexpr (BDIRECT) tmem_ld32(tm_mine + 96, reinterpret_cast<uint32_t(&)[32]>(twr));
+        };
+        auto row_pass1 = [&](double (&xr)[16], double (&xi)[16]) {
+            if constexpr (BDIRECT) {
+                tmem_wait_ld();
+                double2 w[JX_XE_ROWS];
+                w[0] = make_double2(1.0, 0.0);
+#pragma unroll
+                for (int k2 = 1; k2 < JX_XE_ROWS; ++k2)
+                    w[k2] = make_double2(__hiloint2double((int)twr[4 * k2 - 3], (int)twr[4 * k2 - 4]),
+                                         __hiloint2double((int)twr[4 * k2 - 1], (int)twr[4 * k2 - 2]));
+                fft256e_pass1_w(t, xr, xi, w, xbuf, lane_on);
+            } else {
+                fft256e_pass1<32>(t, xr, xi, tw_l, xbuf, lane_on);
+            }
+        };
+
         // ================= phase A1: transform the rows along x, in place
         const int npair = (H + 1) >> 1;
         for (int base = warp * 3; base < npair; base += 3 * NW) {
+            tw_fetch();
             const bool ok = lane_on && base + fg < npair;
             const int u0 = 2 * (base + fg < npair ? base + fg : npair - 1), u1 = u0 + 1;
             const bool has1 = u1 < H;
@@ -237,7 +265,7 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
                 }
                 re[j] = vr; im[j] = vi;
             }
-            fft256e_pass1<32>(t, re, im, tw_l, xbuf, lane_on);
+            row_pass1(re, im);
             __syncwarp();
             fft256_pass2(t, re, im, xbuf, lane_on);
             __syncwarp();
@@ -270,17 +298,14 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
             // four warp groups take a quarter of the rows each; the Nyquist column kx = 128 is shared out by rows.
             static_assert(NT == 512, "direct phase B is laid out for 16 warps");
             const int kx = bkx, u0 = (warp >> 2) * K3_UB;
-            {   // this thread's taps, from tensor memory
-                uint32_t r[64], q[8];
+            {   // this thread's taps, from tensor memory; the Nyquist taps from a 28-entry shared table
+                uint32_t r[64];
                 tmem_ld64(tm_mine + 32, r);
-                tmem_ld8(tm_mine + 96, q);
+#pragma unroll
+                for (int i = 0; i < 7; ++i) ntap[i] = nyqt[7 * nyq_c + i];
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < K3_NB; ++j) tap[j] = __hiloint2double((int)r[2 * j + 1], (int)r[2 * j]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) ntap[j] = __hiloint2double((int)r[2 * (K3_NB + j) + 1], (int)r[2 * (K3_NB + j)]);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) ntap[4 + j] = __hiloint2double((int)q[2 * j + 1], (int)q[2 * j]);
             }
             // Nyquist column kx = 128 first: warp w owns rows 6 w .. 6 w + 5, lane = (row slot, chunk of 7 taps)
             double nyq = 0.0;
@@ -361,6 +386,7 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
         double* tri_w = a.tri + (size_t)w * d.ktri;
         const bool tapq = a.convq != nullptr;                  // parity tap: also keep the full quarter plane
         for (int base = warp * 3; base < npair; base += 3 * NW) {
+            tw_fetch();
             const bool ok = lane_on && base + fg < npair;
             const int u0 = 2 * (base + fg < npair ? base + fg : npair - 1), u1 = u0 + 1;
             const bool has1 = u1 < H;
@@ -370,7 +396,7 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
                 re[j] = lane_on ? xs[u0 * K3_XS + f] : 0.0;
                 im[j] = lane_on && has1 ? xs[u1 * K3_XS + f] : 0.0;
             }
-            fft256e_pass1<32>(t, re, im, tw_l, xbuf, lane_on);
+            row_pass1(re, im);
             __syncwarp();
             fft256_pass2(t, re, im, xbuf, lane_on);
             double* tri0 = tri_w + (u0 * H - ((u0 * (u0 - 1)) >> 1) - u0);     // + v
