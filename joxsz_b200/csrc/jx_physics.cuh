@@ -28,6 +28,7 @@ struct jx_walker_pars {
     double e_core;           // 3 beta - alpha/2
     double e_outer;          // eps/gamma
     double ln_rp, ln_rc, ln_rs, ln_rc2;
+    double inv_rc;           // 1 / r_c
     int dens_double;
 };
 
@@ -54,6 +55,7 @@ JX_HD jx_walker_pars jx_prepare(const double* p, int dens_mode) {
     w.e_core = 3.0 * w.beta - w.alpha / 2.0;
     w.e_outer = w.eps / w.gamma;
     w.ln_rp = log(w.rp); w.ln_rc = log(w.rc); w.ln_rs = log(w.rs); w.ln_rc2 = log(w.rc2);
+    w.inv_rc = 1.0 / w.rc;
     return w;
 }
 
@@ -74,9 +76,9 @@ JX_HD double jx_pressure_only(const jx_walker_pars& w, double lr) {
 }
 
 // n_e(r) (joxsz_funcs.py:389-395): sqrt(n0^2 x^-alpha / ((1+x^2)^(3 beta - alpha/2) (1+(r/rs)^gamma)^(eps/gamma)) [+ 2nd beta model])
-JX_HD double jx_density(const jx_walker_pars& w, double lr) {
+JX_HD double jx_density(const jx_walker_pars& w, double r, double lr) {
     const double lxc = lr - w.ln_rc;
-    const double x2 = exp(2.0 * lxc);
+    const double xr = r * w.inv_rc, x2 = xr * xr;          // (r / r_c)^2 as the reference writes it: no exp
     const double t3 = exp(w.gamma * (lr - w.ln_rs));
     const double ex = -(w.alpha * lxc + w.e_core * log(1.0 + x2) + w.e_outer * log(1.0 + t3));
     if (!w.dens_double) return w.n0 * exp(0.5 * ex);
