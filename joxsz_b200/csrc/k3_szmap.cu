@@ -98,9 +98,11 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
     const uint32_t coef_bytes = (uint32_t)(d.ncoef * sizeof(double));
 
     // ---- one-time set-up of the CTA
-    for (int i = tid; i < JX_XE_ROWS * 32; i += NT) {        // per-lane twiddles [k2][lane]: w256^(t(lane) k2)
-        const int l = i & 31, tl = l < 27 ? l % 9 : l - 27;
-        fft256_make_twiddle((i >> 5) * 16 + tl, tw_s[i]);
+    if constexpr (!BDIRECT) {                                // (the direct variant keeps its twiddles in tensor memory)
+        for (int i = tid; i < JX_XE_ROWS * 32; i += NT) {    // per-lane twiddles [k2][lane]: w256^(t(lane) k2)
+            const int l = i & 31, tl = l < 27 ? l % 9 : l - 27;
+            fft256_make_twiddle((i >> 5) * 16 + tl, tw_s[i]);
+        }
     }
     for (int i = tid; i < hp8 * K3_XS; i += NT) xs[i] = 0.0;
     if (tid == 0) {
