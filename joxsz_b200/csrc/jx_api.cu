@@ -332,7 +332,8 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
                 }
         rc = upload(h, &d.cfrag, t.data(), t.size());
     }
-    if (!rc && d.npad == 256) {
+    d.use_k7 = jx_filter_supported(d) ? 1 : 0;
+    if (!rc && d.use_k7) {
         // filter stage as one GEMM (k7_filter.cu): response of map_out[N//2, N//2 + x] to the convolved-map pixel
         // pair conv_c[u,v] = conv_c[v,u],
         //   R[(u,v), x] = sum_kx (hf[u,kx] cmat[v,kx] + [u != v] hf[v,kx] cmat[u,kx]) dinv[kx, x],
@@ -370,8 +371,8 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     if (!rc) rc = dev_alloc(h, &d.ws_flags, Wm);
     if (!rc) rc = dev_alloc(h, &d.ws_coef, Wm * d.ncoef);
     if (!rc) rc = dev_alloc(h, &d.ws_row, Wm * d.nh);
-    if (!rc && d.npad != 256) rc = dev_alloc(h, &d.ws_g, Wm * d.hp8);
-    if (!rc && d.npad == 256) {
+    if (!rc && !d.use_k7) rc = dev_alloc(h, &d.ws_g, Wm * d.hp8);
+    if (!rc && d.use_k7) {
         rc = dev_alloc(h, &d.ws_tri, Wm * d.ktri);
         // the columns beyond ntri are never written by the map kernel and must not hold NaN patterns (they meet
         // zeros of filt_op); rows of walkers the map kernel skips are never read back
@@ -402,6 +403,7 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
             rc = fail(h, JX_ERR_INVALID, "large-map kernel: geometry does not fit the shared memory of an SM");
         } else {
             cudaError_t e = jx_szmap_large_configure(d);
+            if (e == cudaSuccess && d.use_k7) e = jx_filter_configure(d);
             if (e != cudaSuccess) rc = cuda_fail(h, e, "configure large-map kernel");
             if (!rc) rc = dev_alloc(h, &d.ws_scratch, (size_t)h->sm_count * d.hp8 * d.xs_pitch);
         }
@@ -423,8 +425,8 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
 
 // Map stage + filter stage: spline coefficients -> map_out[N//2, N//2:] as `*nparts` partial rows at `*row`
 // (leading dimension `*ld_row`) for the tail kernel.  Cyclic length 256: shared-memory map kernel writing the packed
-// convolved map, then the filter GEMM over all walkers; 512 / 1024: L2-staged kernel with the filter stage inside,
-// then row = G . dinv.  `ev_mid`, when not NULL, is recorded between the two kernels (stage timers).
+// convolved map, then the filter GEMM over all walkers; 512 / 1024: L2-staged kernel, followed by the same GEMM when
+// the quarter plane fits its tile (nh <= 136) or with the filter stage inside and row = G . dinv otherwise.  `ev_mid`, when not NULL, is recorded between the two kernels (stage timers).
 static cudaError_t launch_map_filter(jx_handle* h, const double* coef, const uint32_t* flags, int W, double* convq,
                                      const double** row, int* ld_row, int* nparts, cudaEvent_t ev_mid, cudaStream_t st) {
     const jx_dev& d = h->d;
@@ -436,9 +438,14 @@ static cudaError_t launch_map_filter(jx_handle* h, const double* coef, const uin
         *row = d.ws_rowp; *ld_row = d.hp8; *nparts = jx_filter_parts(d);
         return jx_launch_filter(d, d.ws_tri, W, d.ws_rowp, st);
     }
-    e = jx_launch_szmap_large(d, coef, flags, W, h->sm_count, convq, d.ws_g, d.ws_scratch, st);
+    e = jx_launch_szmap_large(d, coef, flags, W, h->sm_count, convq, d.use_k7 ? nullptr : d.ws_g,
+                              d.use_k7 ? d.ws_tri : nullptr, d.ws_scratch, st);
     if (e == cudaSuccess && ev_mid) e = cudaEventRecord(ev_mid, st);
     if (e != cudaSuccess) return e;
+    if (d.use_k7) {
+        *row = d.ws_rowp; *ld_row = d.hp8; *nparts = jx_filter_parts(d);
+        return jx_launch_filter(d, d.ws_tri, W, d.ws_rowp, st);
+    }
     *row = d.ws_row; *ld_row = d.nh; *nparts = 1;
     return jx_launch_gemm_nt(d.ws_g, d.hp8, d.dinv_t, d.hp8, d.ws_row, d.nh, W, d.nh, d.hp8, st);
 }

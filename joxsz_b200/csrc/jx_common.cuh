@@ -76,6 +76,7 @@ struct jx_dev {
     const double* g_op_t;    // [nh, nd] g_op transposed (K5 reads it coalesced over the data points)
     const double* dinv_t;    // [nh(v), hp8(kx)] dinv transposed, zero padded: row = G . dinv as an NT GEMM
     // filter stage as one GEMM over the walkers (cyclic length 256; k7_filter.cu)
+    int use_k7;              // filter stage through the GEMM (every cyclic length, as long as nh <= 136)
     int ntri, ktri;          // nh (nh + 1) / 2 pixels u <= v of the quarter plane; rounded up to 32
     const double* filt_op;   // [hp8, ktri] zero padded: filt_op[x, (u,v)] = response of map_out[N//2, N//2 + x] to conv_c[u,v]
     // X-ray
@@ -164,8 +165,9 @@ size_t jx_szmap_smem_bytes(const jx_dev& d);
 bool jx_szmap_large_supported(const jx_dev& d);
 size_t jx_szmap_large_smem_bytes(const jx_dev& d);
 cudaError_t jx_szmap_large_configure(const jx_dev& d);
+// g != NULL: filter stage inside the kernel (G vector out); tri != NULL: packed triangle out for the filter GEMM
 cudaError_t jx_launch_szmap_large(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
-                                  double* convq, double* g, double* scratch, cudaStream_t st);
+                                  double* convq, double* g, double* tri, double* scratch, cudaStream_t st);
 
 // ---- small device helpers
 JX_D double warp_sum(double v) {

@@ -232,9 +232,16 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
                 lin[f] = make_double2(xs[(size_t)u0 * pitch + f], has1 ? xs[(size_t)u1 * pitch + f] : 0.0);
             __syncwarp(gmask);
             group_fft_even<R>(t, gmask, lin, lout, tw_s, twp_s, xbuf);
+            double* tri0 = a.tri ? a.tri + (size_t)w * d.ktri + (u0 * H - ((u0 * (u0 - 1)) >> 1) - u0) : nullptr;   // + v
+            double* tri1 = tri0 + (H - u0 - 1);
             for (int v = t; v < hp16; v += 16) {
                 const bool in = v < H;
                 const double2 o = lout[v < Q ? v : 0];
+                if (tri0) {          // packed triangle for the filter GEMM; the scratch copy only feeds the tap
+                    if (in && v >= u0) tri0[v] = o.x;
+                    if (in && has1 && v >= u1) tri1[v] = o.y;
+                    if (!a.convq) continue;
+                }
                 xs[(size_t)u0 * pitch + v] = in ? o.x : 0.0;
                 if (has1) xs[(size_t)u1 * pitch + v] = in ? o.y : 0.0;
             }
@@ -247,8 +254,8 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
             for (int i = tid; i < H * H; i += NT) cq[i] = xs[(size_t)(i / H) * pitch + (i % H)];
         }
 
-        // ---- D: G[kx] on the FP64 tensor cores, conv_c read from the scratch (L2)
-        {
+        // ---- D: G[kx] on the FP64 tensor cores, conv_c read from the scratch (L2); skipped when the filter GEMM follows
+        if (a.g) {
             const int nsplit = k3_run_phase_d<0>(d, xs, pitch, gpart_s, warp, lane, NT / 32);
             __syncthreads();
             for (int k = tid; k < hp8; k += NT) {
@@ -282,10 +289,10 @@ cudaError_t jx_szmap_large_configure(const jx_dev& d) {
 
 // scratch: [min(W, sm_count)][hp8][xs_pitch] doubles
 cudaError_t jx_launch_szmap_large(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
-                                  double* convq, double* g, double* scratch, cudaStream_t st) {
+                                  double* convq, double* g, double* tri, double* scratch, cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
     k3_args a;
-    a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.g = g; a.scratch = scratch;
+    a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.g = g; a.tri = tri; a.scratch = scratch;
     const int nt = k3l_pick_threads(d);
     const size_t smem = k3l_layout(d, nt).total;
     const int grid = W < sm_count ? W : sm_count;
