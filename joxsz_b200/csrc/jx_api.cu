@@ -214,9 +214,10 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     UP(dx, s->dx, H * H);
     UP(bhat, s->bhat, Q * Q);
     d.nbeam = s->nbeam;
-    if (!rc && s->bmix && s->nbeam >= 1 && s->nbeam <= JX_BMIX_ROWS && Q <= JX_BMIX_PITCH) {
-        std::vector<double> t((size_t)JX_BMIX_ROWS * JX_BMIX_PITCH, 0.0);
-        for (int j = 0; j < s->nbeam; ++j) memcpy(&t[(size_t)j * JX_BMIX_PITCH], s->bmix + (size_t)j * Q, sizeof(double) * Q);
+    if (!rc && s->bmix && s->nbeam >= 1 && s->nbeam <= JX_BMIX_ROWS) {
+        d.bmix_pitch = s->npad == 256 ? JX_BMIX_PITCH : ((Q + 3) & ~3);
+        std::vector<double> t((size_t)JX_BMIX_ROWS * d.bmix_pitch, 0.0);
+        for (int j = 0; j < s->nbeam; ++j) memcpy(&t[(size_t)j * d.bmix_pitch], s->bmix + (size_t)j * Q, sizeof(double) * Q);
         rc = upload(h, &d.bmix, t.data(), t.size());
     }
     UP(hf, s->hf, H * H);
@@ -406,6 +407,7 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
             if (e == cudaSuccess && d.use_k7) e = jx_filter_configure(d);
             if (e != cudaSuccess) rc = cuda_fail(h, e, "configure large-map kernel");
             if (!rc) rc = dev_alloc(h, &d.ws_scratch, (size_t)h->sm_count * d.hp8 * d.xs_pitch);
+            if (!rc && d.bmix) rc = dev_alloc(h, &d.ws_scratch2, (size_t)h->sm_count * d.hp8 * d.xs_pitch);
         }
     }
     if (!rc) {
@@ -439,7 +441,7 @@ static cudaError_t launch_map_filter(jx_handle* h, const double* coef, const uin
         return jx_launch_filter(d, d.ws_tri, W, d.ws_rowp, st);
     }
     e = jx_launch_szmap_large(d, coef, flags, W, h->sm_count, convq, d.use_k7 ? nullptr : d.ws_g,
-                              d.use_k7 ? d.ws_tri : nullptr, d.ws_scratch, st);
+                              d.use_k7 ? d.ws_tri : nullptr, d.ws_scratch, d.ws_scratch2, st);
     if (e == cudaSuccess && ev_mid) e = cudaEventRecord(ev_mid, st);
     if (e != cudaSuccess) return e;
     if (d.use_k7) {

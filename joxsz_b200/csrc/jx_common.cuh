@@ -49,7 +49,8 @@ struct jx_dev {
     const double* bhat;      // [nq, nq]
     int nbeam;               // beam half-side incl. the centre
     int k3_direct;           // map kernel convolves along y directly (jx_szmap_direct_ok at jx_create)
-    const double* bmix;      // [28, JX_BMIX_PITCH] beam in (y offset, kx), zero rows beyond nbeam; NULL when nbeam > 28
+    const double* bmix;      // [28, bmix_pitch] beam in (y offset, kx), zero rows beyond nbeam; NULL when nbeam > 28
+    int bmix_pitch;          // JX_BMIX_PITCH for the cyclic length 256, nq rounded up to 4 otherwise
     const double* cmat_t;    // [nh, nh] transposed on upload: [kx, v]
     const double* hf;        // [nh, nh] [u, kx]
     const double* dinv;      // [nh, nh] [kx, v]
@@ -58,6 +59,7 @@ struct jx_dev {
     int hp8, hp16;           // nh rounded up to 8 / 16
     int xs_pitch;            // large-map path: doubles per row of the per-CTA scratch map (even, >= nq and hp16)
     double* ws_scratch;      // large-map path: [sm_count][hp8][xs_pitch]
+    double* ws_scratch2;     // large-map path, direct y convolution: its output map, same shape
     const uint16_t* seg16;   // [nh, nh] seg narrowed
     const double* costab;    // [nmap] cos(2 pi m / nmap)
     const double* hf_pad;    // [hp8, hp8] hf zero padded
@@ -167,7 +169,8 @@ size_t jx_szmap_large_smem_bytes(const jx_dev& d);
 cudaError_t jx_szmap_large_configure(const jx_dev& d);
 // g != NULL: filter stage inside the kernel (G vector out); tri != NULL: packed triangle out for the filter GEMM
 cudaError_t jx_launch_szmap_large(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
-                                  double* convq, double* g, double* tri, double* scratch, cudaStream_t st);
+                                  double* convq, double* g, double* tri, double* scratch, double* scratch2,
+                                  cudaStream_t st);
 
 // ---- small device helpers
 JX_D double warp_sum(double v) {

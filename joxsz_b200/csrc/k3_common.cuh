@@ -14,6 +14,7 @@ struct k3_args {
     double *convq, *g;    // g: large-map path (filter stage in the kernel); convq: parity tap
     double* tri;          // shared-memory path: packed u <= v triangle of the convolved map, [W][d.ktri]
     double* scratch;      // large-map path only: [gridDim.x][hp8][pitch] doubles
+    double* scratch2;     // large-map path, direct y convolution: second map of the same shape (NULL: FFT form)
 };
 
 JX_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -94,6 +94,25 @@ JX_D void group_fft_even(int t, unsigned gmask, const double2* __restrict__ in, 
     __syncwarp(gmask);
 }
 
+// Direct y convolution of UB consecutive rows u0 .. u0 + UB - 1 of column kx of the map `in` (row pitch `pitch`, in
+// the L2-resident scratch): acc[k] = sum_j tap[|j|] ext(in)[u0 + k - j, kx]; same scheme as k3_szmap.cu's phase B.
+constexpr int K3L_NB = JX_BMIX_ROWS, K3L_UB = 32;
+JX_D void k3l_yconv(const double* __restrict__ in, int pitch, int kx, int u0, int H, const double (&tap)[K3L_NB],
+                    double (&acc)[K3L_UB]) {
+#pragma unroll
+    for (int k = 0; k < K3L_UB; ++k) acc[k] = 0.0;
+#pragma unroll
+    for (int ii = 0; ii < K3L_UB + 2 * (K3L_NB - 1); ++ii) {
+        const int up = u0 - (K3L_NB - 1) + ii, ua = up < 0 ? -up : up;
+        const double x = ua < H ? in[(size_t)ua * pitch + kx] : 0.0;
+#pragma unroll
+        for (int k = 0; k < K3L_UB; ++k) {
+            const int j = ii - (K3L_NB - 1) - k < 0 ? k + (K3L_NB - 1) - ii : ii - (K3L_NB - 1) - k;
+            if (j < K3L_NB) acc[k] = fma(tap[j], x, acc[k]);
+        }
+    }
+}
+
 template <int R>
 __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant__ k3_args a) {
     extern __shared__ __align__(128) unsigned char k3l_raw[];
@@ -119,6 +138,10 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
     const uint32_t coef_bytes = (uint32_t)(d.ncoef * sizeof(double));
     const int pitch = d.xs_pitch;                               // doubles per row of the scratch map
     double* xs = a.scratch + (size_t)blockIdx.x * hp8 * pitch;
+    // direct y convolution (beam of at most 28 samples per side): out of place into a second map, which the later
+    // phases then use
+    const bool bdirect = a.scratch2 != nullptr;
+    double* xc = bdirect ? a.scratch2 + (size_t)blockIdx.x * hp8 * pitch : xs;
 
     for (int i = tid; i < 256; i += NT) fft256_make_twiddle(i, tw_s[i]);
     for (int i = tid; i < P; i += NT) {
@@ -127,6 +150,8 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
         twp_s[i] = make_double2(cos(ang), sin(ang));
     }
     for (int i = tid; i < hp8 * pitch; i += NT) xs[i] = 0.0;
+    if (bdirect)
+        for (int i = tid; i < hp8 * pitch; i += NT) xc[i] = 0.0;
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
@@ -198,8 +223,27 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
         }
         __syncthreads();
 
-        // ---- B: columns -- cyclic convolution with the beam along y (beam spectrum is symmetric: row kx is read)
-        const int ncpair = (Q + 1) >> 1;
+        // ---- B: beam convolution along y.  Direct form: 55-tap FMA streams, lane = column, tasks of 32 rows x 32
+        // columns dealt to the warps (about a quarter of the FP64 work of the two full-complex column FFTs, and no
+        // staging through shared memory)
+        if (bdirect) {
+            const int ncw = (Q + 31) >> 5, nrb = (H + K3L_UB - 1) / K3L_UB;
+            for (int task = warp; task < ncw * nrb; task += (NT >> 5)) {
+                const int cw = task % ncw, u0 = (task / ncw) * K3L_UB;
+                const int kx = 32 * cw + lane;
+                const bool on = kx < Q;
+                const int kxc = on ? kx : Q - 1;
+                double tap[K3L_NB], acc[K3L_UB];
+#pragma unroll
+                for (int j = 0; j < K3L_NB; ++j) tap[j] = __ldg(d.bmix + (size_t)j * d.bmix_pitch + kxc);
+                k3l_yconv(xs, pitch, kxc, u0, H, tap, acc);
+#pragma unroll
+                for (int k = 0; k < K3L_UB; ++k)
+                    if (on && u0 + k < H) xc[(size_t)(u0 + k) * pitch + kx] = acc[k];
+            }
+        }
+        // FFT form: cyclic convolution with the beam spectrum (symmetric: row kx is read), any beam size
+        const int ncpair = bdirect ? 0 : (Q + 1) >> 1;
         for (int cp = grp; cp < ncpair; cp += ngroups) {
             const int kx = 2 * cp;
             const bool has1 = kx + 1 < Q;
@@ -229,7 +273,7 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
             const int u0 = 2 * rp, u1 = u0 + 1;
             const bool has1 = u1 < H;
             for (int f = t; f < Q; f += 16)
-                lin[f] = make_double2(xs[(size_t)u0 * pitch + f], has1 ? xs[(size_t)u1 * pitch + f] : 0.0);
+                lin[f] = make_double2(xc[(size_t)u0 * pitch + f], has1 ? xc[(size_t)u1 * pitch + f] : 0.0);
             __syncwarp(gmask);
             group_fft_even<R>(t, gmask, lin, lout, tw_s, twp_s, xbuf);
             double* tri0 = a.tri ? a.tri + (size_t)w * d.ktri + (u0 * H - ((u0 * (u0 - 1)) >> 1) - u0) : nullptr;   // + v
@@ -242,8 +286,8 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
                     if (in && has1 && v >= u1) tri1[v] = o.y;
                     if (!a.convq) continue;
                 }
-                xs[(size_t)u0 * pitch + v] = in ? o.x : 0.0;
-                if (has1) xs[(size_t)u1 * pitch + v] = in ? o.y : 0.0;
+                xc[(size_t)u0 * pitch + v] = in ? o.x : 0.0;
+                if (has1) xc[(size_t)u1 * pitch + v] = in ? o.y : 0.0;
             }
             __syncwarp(gmask);
         }
@@ -251,12 +295,12 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
 
         if (a.convq) {
             double* cq = a.convq + (size_t)w * H * H;
-            for (int i = tid; i < H * H; i += NT) cq[i] = xs[(size_t)(i / H) * pitch + (i % H)];
+            for (int i = tid; i < H * H; i += NT) cq[i] = xc[(size_t)(i / H) * pitch + (i % H)];
         }
 
         // ---- D: G[kx] on the FP64 tensor cores, conv_c read from the scratch (L2); skipped when the filter GEMM follows
         if (a.g) {
-            const int nsplit = k3_run_phase_d<0>(d, xs, pitch, gpart_s, warp, lane, NT / 32);
+            const int nsplit = k3_run_phase_d<0>(d, xc, pitch, gpart_s, warp, lane, NT / 32);
             __syncthreads();
             for (int k = tid; k < hp8; k += NT) {
                 double g = gpart_s[k];
@@ -289,10 +333,11 @@ cudaError_t jx_szmap_large_configure(const jx_dev& d) {
 
 // scratch: [min(W, sm_count)][hp8][xs_pitch] doubles
 cudaError_t jx_launch_szmap_large(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
-                                  double* convq, double* g, double* tri, double* scratch, cudaStream_t st) {
+                                  double* convq, double* g, double* tri, double* scratch, double* scratch2,
+                                  cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
     k3_args a;
-    a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.g = g; a.tri = tri; a.scratch = scratch;
+    a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.g = g; a.tri = tri; a.scratch = scratch; a.scratch2 = scratch2;
     const int nt = k3l_pick_threads(d);
     const size_t smem = k3l_layout(d, nt).total;
     const int grid = W < sm_count ? W : sm_count;
