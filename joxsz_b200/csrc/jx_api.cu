@@ -256,11 +256,6 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
         rc = upload(h, &d.costab, c.data(), c.size());
     }
     if (!rc) {
-        std::vector<double> t((size_t)d.hp8 * d.hp8, 0.0);
-        for (int u = 0; u < H; ++u) memcpy(&t[(size_t)u * d.hp8], s->hf + (size_t)u * H, sizeof(double) * H);
-        rc = upload(h, &d.hf_pad, t.data(), t.size());
-    }
-    if (!rc) {
         std::vector<double> t(s->nr, 0.0);
         if (s->w_integ) memcpy(t.data(), s->w_integ, sizeof(double) * s->nr);
         rc = upload(h, &d.w_integ, t.data(), t.size());
@@ -280,12 +275,6 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
         for (int dp = 0; dp < s->nd; ++dp)
             for (int v = 0; v < H; ++v) t[(size_t)v * s->nd + dp] = s->g_op[(size_t)dp * H + v];
         rc = upload(h, &d.g_op_t, t.data(), t.size());
-    }
-    if (!rc) {
-        std::vector<double> t((size_t)H * d.hp8, 0.0);
-        for (int kx = 0; kx < H; ++kx)
-            for (int v = 0; v < H; ++v) t[(size_t)v * d.hp8 + kx] = s->dinv[(size_t)kx * H + v];
-        rc = upload(h, &d.dinv_t, t.data(), t.size());
     }
     if (!rc) {   // synthesis table: pixels with u <= v, in thread order, padded to a multiple of the CTA size
         std::vector<jx_synth_px> t;
@@ -319,46 +308,66 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
         rc = upload(h, &dev, t.data(), t.size());
         d.bhat_sw = reinterpret_cast<const double2*>(dev);
     }
-    if (!rc) {   // phase-D cosine matrix in mma.m8n8k4 B-fragment order: [kx tile][k step][lane]
-        const int ntile = d.hp8 / 8, nks = d.hp8 / 4;
-        std::vector<double> t((size_t)ntile * nks * 32, 0.0);
-        for (int jt = 0; jt < ntile; ++jt)
-            for (int ks = 0; ks < nks; ++ks)
-                for (int lane = 0; lane < 32; ++lane) {
-                    const int kx = jt * 8 + (lane >> 2), fk = lane & 3;
-                    const int v = 8 * (ks >> 1) + 2 * (ks & 1) + (fk & 1) + 4 * (fk >> 1);
-                    if (kx < H && v < H)
-                        t[((size_t)jt * nks + ks) * 32 + lane] =
-                            cos(2.0 * M_PI * (double)(((long long)kx * v) % s->nmap) / (double)s->nmap) * (v ? 2.0 : 1.0);
-                }
-        rc = upload(h, &d.cfrag, t.data(), t.size());
-    }
-    d.use_k7 = jx_filter_supported(d) ? 1 : 0;
-    if (!rc && d.use_k7) {
+    if (!rc) {
         // filter stage as one GEMM (k7_filter.cu): response of map_out[N//2, N//2 + x] to the convolved-map pixel
         // pair conv_c[u,v] = conv_c[v,u],
-        //   R[(u,v), x] = sum_kx (hf[u,kx] cmat[v,kx] + [u != v] hf[v,kx] cmat[u,kx]) dinv[kx, x],
-        // accumulated in long double so that the operator is correctly rounded to double
+        //   R[(u,v), x] = sum_kx F[(u,v), kx] dinv[kx, x],   F = hf[u,kx] cmat[v,kx] + [u != v] hf[v,kx] cmat[u,kx],
+        // stored as filt_op[x, (u,v)] with the output index padded to hpf rows and the pixel index to ktri columns
         d.ntri = H * (H + 1) / 2;
         d.ktri = (d.ntri + 31) & ~31;
-        std::vector<double> t((size_t)d.hp8 * d.ktri, 0.0);
-        std::vector<long double> f(H), dv((size_t)H * H);
-        for (int i = 0; i < H * H; ++i) dv[i] = (long double)s->dinv[i];
-        size_t idx = 0;
-        for (int u = 0; u < H; ++u)
-            for (int v = u; v < H; ++v, ++idx) {
-                for (int kx = 0; kx < H; ++kx) {
-                    long double e = (long double)s->hf[(size_t)u * H + kx] * (long double)s->cmat[(size_t)v * H + kx];
-                    if (u != v) e += (long double)s->hf[(size_t)v * H + kx] * (long double)s->cmat[(size_t)u * H + kx];
-                    f[kx] = e;
+        d.hpf = jx_filter_pitch(d.hp8);
+        if (H <= 136) {
+            // host, accumulated in long double so that the operator is correctly rounded to double
+            std::vector<double> t((size_t)d.hpf * d.ktri, 0.0);
+            std::vector<long double> f(H), dv((size_t)H * H);
+            for (int i = 0; i < H * H; ++i) dv[i] = (long double)s->dinv[i];
+            size_t idx = 0;
+            for (int u = 0; u < H; ++u)
+                for (int v = u; v < H; ++v, ++idx) {
+                    for (int kx = 0; kx < H; ++kx) {
+                        long double e = (long double)s->hf[(size_t)u * H + kx] * (long double)s->cmat[(size_t)v * H + kx];
+                        if (u != v) e += (long double)s->hf[(size_t)v * H + kx] * (long double)s->cmat[(size_t)u * H + kx];
+                        f[kx] = e;
+                    }
+                    for (int x = 0; x < H; ++x) {
+                        long double acc = 0.0L;
+                        for (int kx = 0; kx < H; ++kx) acc += f[kx] * dv[(size_t)kx * H + x];
+                        t[(size_t)x * d.ktri + idx] = (double)acc;
+                    }
                 }
-                for (int x = 0; x < H; ++x) {
-                    long double acc = 0.0L;
-                    for (int kx = 0; kx < H; ++kx) acc += f[kx] * dv[(size_t)kx * H + x];
-                    t[(size_t)x * d.ktri + idx] = (double)acc;
-                }
+            rc = upload(h, &d.filt_op, t.data(), t.size());
+        } else {
+            // wide quarter planes (the 511-pixel maps: 32 896 pixels x 256 outputs): F on the host, the product with
+            // dinv on the device by the DMMA GEMM, filt_op[x, :] = sum_kx dinv[kx, x] F[:, kx]
+            double *fdev = nullptr, *ddev = nullptr, *op = nullptr;
+            {
+                std::vector<double> f((size_t)d.ktri * d.hp8, 0.0);
+                size_t idx = 0;
+                for (int u = 0; u < H; ++u)
+                    for (int v = u; v < H; ++v, ++idx)
+                        for (int kx = 0; kx < H; ++kx) {
+                            double e = s->hf[(size_t)u * H + kx] * s->cmat[(size_t)v * H + kx];
+                            if (u != v) e += s->hf[(size_t)v * H + kx] * s->cmat[(size_t)u * H + kx];
+                            f[idx * d.hp8 + kx] = e;
+                        }
+                std::vector<double> dt((size_t)d.hpf * d.hp8, 0.0);
+                for (int kx = 0; kx < H; ++kx)
+                    for (int x = 0; x < H; ++x) dt[(size_t)x * d.hp8 + kx] = s->dinv[(size_t)kx * H + x];
+                const double *fc = nullptr, *dc = nullptr;
+                rc = upload(h, &fc, f.data(), f.size());
+                if (!rc) rc = upload(h, &dc, dt.data(), dt.size());
+                fdev = const_cast<double*>(fc); ddev = const_cast<double*>(dc);
             }
-        rc = upload(h, &d.filt_op, t.data(), t.size());
+            if (!rc) rc = dev_alloc(h, &op, (size_t)d.hpf * d.ktri);
+            if (!rc) {
+                cudaError_t e = jx_gemm_configure();
+                if (e == cudaSuccess) e = cudaMemset(op, 0, (size_t)d.hpf * d.ktri * sizeof(double));
+                if (e == cudaSuccess) e = jx_launch_gemm_nt(ddev, d.hp8, fdev, d.hp8, op, d.ktri, d.hpf, d.ktri, d.hp8, 0);
+                if (e == cudaSuccess) e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) rc = cuda_fail(h, e, "filter operator on the device");
+            }
+            d.filt_op = op;
+        }
     }
     // workspace
     const size_t Wm = (size_t)s->max_walkers;
@@ -371,15 +380,13 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     if (!rc) rc = dev_alloc(h, &d.ws_xlike, Wm);
     if (!rc) rc = dev_alloc(h, &d.ws_flags, Wm);
     if (!rc) rc = dev_alloc(h, &d.ws_coef, Wm * d.ncoef);
-    if (!rc) rc = dev_alloc(h, &d.ws_row, Wm * d.nh);
-    if (!rc && !d.use_k7) rc = dev_alloc(h, &d.ws_g, Wm * d.hp8);
-    if (!rc && d.use_k7) {
+    if (!rc) {
         rc = dev_alloc(h, &d.ws_tri, Wm * d.ktri);
         // the columns beyond ntri are never written by the map kernel and must not hold NaN patterns (they meet
         // zeros of filt_op); rows of walkers the map kernel skips are never read back
         if (!rc && cudaMemset(d.ws_tri, 0, Wm * d.ktri * sizeof(double)) != cudaSuccess)
             rc = fail(h, JX_ERR_CUDA, "cudaMemset(ws_tri)");
-        if (!rc) rc = dev_alloc(h, &d.ws_rowp, (size_t)jx_filter_parts(d) * Wm * d.hp8);
+        if (!rc) rc = dev_alloc(h, &d.ws_rowp, (size_t)jx_filter_parts(d) * Wm * d.hpf);
     }
     if (!rc) {
         cudaError_t e = jx_profiles_configure(d);
@@ -390,8 +397,6 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
         size_t smem = jx_szmap_smem_bytes(d);
         if (smem > (size_t)prop.sharedMemPerBlockOptin) {
             rc = fail(h, JX_ERR_INVALID, "map kernel needs more shared memory than the device offers");
-        } else if (!jx_filter_supported(d)) {
-            rc = fail(h, JX_ERR_INVALID, "filter GEMM: map quarter plane wider than 136 pixels");
         } else {
             d.k3_direct = jx_szmap_direct_ok(d) ? 1 : 0;
             cudaError_t e = jx_szmap_configure(d);
@@ -404,7 +409,7 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
             rc = fail(h, JX_ERR_INVALID, "large-map kernel: geometry does not fit the shared memory of an SM");
         } else {
             cudaError_t e = jx_szmap_large_configure(d);
-            if (e == cudaSuccess && d.use_k7) e = jx_filter_configure(d);
+            if (e == cudaSuccess) e = jx_filter_configure(d);
             if (e != cudaSuccess) rc = cuda_fail(h, e, "configure large-map kernel");
             if (!rc) rc = dev_alloc(h, &d.ws_scratch, (size_t)h->sm_count * d.hp8 * d.xs_pitch);
             if (!rc && d.bmix) rc = dev_alloc(h, &d.ws_scratch2, (size_t)h->sm_count * d.hp8 * d.xs_pitch);
@@ -427,8 +432,7 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
 
 // Map stage + filter stage: spline coefficients -> map_out[N//2, N//2:] as `*nparts` partial rows at `*row`
 // (leading dimension `*ld_row`) for the tail kernel.  Cyclic length 256: shared-memory map kernel writing the packed
-// convolved map, then the filter GEMM over all walkers; 512 / 1024: L2-staged kernel, followed by the same GEMM when
-// the quarter plane fits its tile (nh <= 136) or with the filter stage inside and row = G . dinv otherwise.  `ev_mid`, when not NULL, is recorded between the two kernels (stage timers).
+// convolved map, then the filter GEMM over all walkers; 512 / 1024: L2-staged kernel, followed by the same GEMM.  `ev_mid`, when not NULL, is recorded between the two kernels (stage timers).
 static cudaError_t launch_map_filter(jx_handle* h, const double* coef, const uint32_t* flags, int W, double* convq,
                                      const double** row, int* ld_row, int* nparts, cudaEvent_t ev_mid, cudaStream_t st) {
     const jx_dev& d = h->d;
@@ -437,19 +441,14 @@ static cudaError_t launch_map_filter(jx_handle* h, const double* coef, const uin
         e = jx_launch_szmap(d, coef, flags, W, h->sm_count, convq, d.ws_tri, st);
         if (e == cudaSuccess && ev_mid) e = cudaEventRecord(ev_mid, st);
         if (e != cudaSuccess) return e;
-        *row = d.ws_rowp; *ld_row = d.hp8; *nparts = jx_filter_parts(d);
+        *row = d.ws_rowp; *ld_row = d.hpf; *nparts = jx_filter_parts(d);
         return jx_launch_filter(d, d.ws_tri, W, d.ws_rowp, st);
     }
-    e = jx_launch_szmap_large(d, coef, flags, W, h->sm_count, convq, d.use_k7 ? nullptr : d.ws_g,
-                              d.use_k7 ? d.ws_tri : nullptr, d.ws_scratch, d.ws_scratch2, st);
+    e = jx_launch_szmap_large(d, coef, flags, W, h->sm_count, convq, d.ws_tri, d.ws_scratch, d.ws_scratch2, st);
     if (e == cudaSuccess && ev_mid) e = cudaEventRecord(ev_mid, st);
     if (e != cudaSuccess) return e;
-    if (d.use_k7) {
-        *row = d.ws_rowp; *ld_row = d.hp8; *nparts = jx_filter_parts(d);
-        return jx_launch_filter(d, d.ws_tri, W, d.ws_rowp, st);
-    }
-    *row = d.ws_row; *ld_row = d.nh; *nparts = 1;
-    return jx_launch_gemm_nt(d.ws_g, d.hp8, d.dinv_t, d.hp8, d.ws_row, d.nh, W, d.nh, d.hp8, st);
+    *row = d.ws_rowp; *ld_row = d.hpf; *nparts = jx_filter_parts(d);
+    return jx_launch_filter(d, d.ws_tri, W, d.ws_rowp, st);
 }
 
 // ------------------------------------------------------------------------------------------------

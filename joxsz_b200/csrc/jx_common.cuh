@@ -62,11 +62,9 @@ struct jx_dev {
     double* ws_scratch2;     // large-map path, direct y convolution: its output map, same shape
     const uint16_t* seg16;   // [nh, nh] seg narrowed
     const double* costab;    // [nmap] cos(2 pi m / nmap)
-    const double* hf_pad;    // [hp8, hp8] hf zero padded
     const jx_synth_px* synth; // [nsynth] quarter-plane pixels with u <= v, padded with u = 0xffff sentinels
     int nsynth;               // multiple of 256
     const double2* bhat_sw;  // [ceil(nq/2)][16][9] beam spectrum of column pair cp in FFT thread order (K3 phase B: position p, thread t = 0..8)
-    const double* cfrag;     // [hp8/8][hp8/4][32] w_v cos(2 pi kx v / N) in DMMA B-fragment order (K3 phase D)
     const double* w_t0;      // [nt]
     int nconv;
     const double *conv_T, *conv_I;
@@ -76,11 +74,10 @@ struct jx_dev {
     const double* w_integ;   // [nr] (zeros when the operator was not supplied)
     double integ_mu, integ_sig;
     const double* g_op_t;    // [nh, nd] g_op transposed (K5 reads it coalesced over the data points)
-    const double* dinv_t;    // [nh(v), hp8(kx)] dinv transposed, zero padded: row = G . dinv as an NT GEMM
     // filter stage as one GEMM over the walkers (cyclic length 256; k7_filter.cu)
-    int use_k7;              // filter stage through the GEMM (every cyclic length, as long as nh <= 136)
+    int hpf;                 // leading dimension of filt_op's output index and of the partial rows (>= hp8)
     int ntri, ktri;          // nh (nh + 1) / 2 pixels u <= v of the quarter plane; rounded up to 32
-    const double* filt_op;   // [hp8, ktri] zero padded: filt_op[x, (u,v)] = response of map_out[N//2, N//2 + x] to conv_c[u,v]
+    const double* filt_op;   // [hpf, ktri] zero padded: filt_op[x, (u,v)] = response of map_out[N//2, N//2 + x] to conv_c[u,v]
     // X-ray
     int na, nb, ntab;
     const double *midpt_kpc, *projvols, *tlog, *lnrate0, *lnrate1, *cts, *srcscale, *bkgterm;
@@ -96,10 +93,8 @@ struct jx_dev {
     double* ws_xlike;   // [W]
     uint32_t* ws_flags; // [W]
     double* ws_coef;    // [W, ncoef]
-    double* ws_row;     // [W, nh]  map_out[N//2, N//2:]
-    double* ws_g;       // [W, hp8] G[kx] written by the large-map kernel
     double* ws_tri;     // [W, ktri] packed triangle of the convolved map (map kernel -> filter GEMM), zero padded
-    double* ws_rowp;    // [jx_filter_parts(d) * W, hp8] K-split partial sums of the filter GEMM
+    double* ws_rowp;    // [jx_filter_parts(d) * W, hpf] K-split partial sums of the filter GEMM
     double* ws_convq;   // tap only, allocated lazily: [W, nh, nh]
 };
 
@@ -146,7 +141,7 @@ cudaError_t jx_launch_szmap(const jx_dev& d, const double* coef, const uint32_t*
                             double* convq, double* tri, cudaStream_t st);
 // filter stage (k7_filter.cu): rowp[kparts][W][hp8] = K-split partial sums of tri[W, ktri] . filt_op^T
 constexpr int JX_FILTER_CPP = 13;         // chunks of 32 packed pixels per K part
-bool jx_filter_supported(const jx_dev& d);
+int jx_filter_pitch(int hp8);
 cudaError_t jx_filter_configure(const jx_dev& d);
 int jx_filter_parts(const jx_dev& d);     // ws_rowp holds jx_filter_parts(d) * max_walkers rows
 cudaError_t jx_launch_filter(const jx_dev& d, const double* tri, int W, double* rowp, cudaStream_t st);
@@ -167,10 +162,8 @@ size_t jx_szmap_smem_bytes(const jx_dev& d);
 bool jx_szmap_large_supported(const jx_dev& d);
 size_t jx_szmap_large_smem_bytes(const jx_dev& d);
 cudaError_t jx_szmap_large_configure(const jx_dev& d);
-// g != NULL: filter stage inside the kernel (G vector out); tri != NULL: packed triangle out for the filter GEMM
 cudaError_t jx_launch_szmap_large(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
-                                  double* convq, double* g, double* tri, double* scratch, double* scratch2,
-                                  cudaStream_t st);
+                                  double* convq, double* tri, double* scratch, double* scratch2, cudaStream_t st);
 
 // ---- small device helpers
 JX_D double warp_sum(double v) {

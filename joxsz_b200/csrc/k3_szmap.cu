@@ -549,7 +549,7 @@ cudaError_t jx_launch_szmap(const jx_dev& d, const double* coef, const uint32_t*
                             double* convq, double* tri, cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
     k3_args a;
-    a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.g = nullptr; a.tri = tri; a.scratch = nullptr; a.scratch2 = nullptr;
+    a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.tri = tri; a.scratch = nullptr; a.scratch2 = nullptr;
     const int grid = W < sm_count ? W : sm_count;
     return k3_dispatch(d, [&](auto kern, int nt) {
         kern<<<grid, nt, k3_layout(d, d.hp8, nt).total, st>>>(a);

@@ -1,6 +1,6 @@
 // K3L -- the map stage for maps whose cyclic convolution length is 512 or 1024 (map sides up to ~1000 pixels):
-// same mathematics and phases as k3_szmap.cu (synthesis, row transforms, column convolution with the beam
-// spectrum, rows back, DMMA filter stage; reference joxsz_funcs.py:462-467), but the per-walker quarter-plane
+// same mathematics and phases as k3_szmap.cu (synthesis, row transforms, beam convolution along y, rows back, packed
+// triangle out for the filter GEMM; reference joxsz_funcs.py:462-464), but the per-walker quarter-plane
 // working set (H x (P/2+1) doubles: 264 KB at N = 255, 1 MB at N = 511) no longer fits the shared memory of an
 // SM, so it lives in a per-CTA global scratch that stays resident in the 126 MB L2, and each 16-thread group
 // stages one line (row pair or column pair) at a time through shared memory.
@@ -17,7 +17,7 @@
 namespace {
 
 struct k3l_smem_layout {
-    size_t tw, twp, lines, xbuf, coef, gpart, mbar, total;
+    size_t tw, twp, lines, xbuf, coef, mbar, total;
     int lq;     // padded line length (complex elements)
 };
 
@@ -32,7 +32,6 @@ __host__ __device__ inline k3l_smem_layout k3l_layout(const jx_dev& d, int nthre
     L.lines = take((size_t)groups * 2 * L.lq * sizeof(double2));       // input + output line per group
     L.xbuf = take((size_t)groups * JX_XB_ELEMS * sizeof(double2));
     L.coef = take((size_t)2 * d.ncoef * sizeof(double));
-    L.gpart = take((size_t)JX_D_MAXSPLIT * d.hp8 * sizeof(double));
     L.mbar = take(2 * sizeof(uint64_t));
     L.total = o;
     return L;
@@ -119,14 +118,13 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
     constexpr int P = 256 * R, Q = P / 2 + 1;
     const jx_dev& d = a.d;
     const int NT = blockDim.x;
-    const int H = d.nh, hp8 = d.hp8, hp16 = d.hp16;
+    const int H = d.nh, hp8 = d.hp8;
     const k3l_smem_layout L = k3l_layout(d, NT);
     double2* tw_s = reinterpret_cast<double2*>(k3l_raw + L.tw);
     double2* twp_s = reinterpret_cast<double2*>(k3l_raw + L.twp);
     double2* lines = reinterpret_cast<double2*>(k3l_raw + L.lines);
     double2* xbuf_all = reinterpret_cast<double2*>(k3l_raw + L.xbuf);
     double* coef_s = reinterpret_cast<double*>(k3l_raw + L.coef);
-    double* gpart_s = reinterpret_cast<double*>(k3l_raw + L.gpart);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(k3l_raw + L.mbar);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -268,7 +266,7 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
         }
         __syncthreads();
 
-        // ---- C: rows back to pixel space, in place: xs[u, v] = conv_c[u, v] (zero beyond H up to the K padding)
+        // ---- C: rows back to pixel space
         for (int rp = grp; rp < npair; rp += ngroups) {
             const int u0 = 2 * rp, u1 = u0 + 1;
             const bool has1 = u1 < H;
@@ -276,18 +274,18 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
                 lin[f] = make_double2(xc[(size_t)u0 * pitch + f], has1 ? xc[(size_t)u1 * pitch + f] : 0.0);
             __syncwarp(gmask);
             group_fft_even<R>(t, gmask, lin, lout, tw_s, twp_s, xbuf);
-            double* tri0 = a.tri ? a.tri + (size_t)w * d.ktri + (u0 * H - ((u0 * (u0 - 1)) >> 1) - u0) : nullptr;   // + v
+            // conv_c[u, v] for v >= u goes to the packed triangle of this walker (row u starts at u H - u (u - 1) / 2);
+            // the in-place copy only feeds the parity tap
+            double* tri0 = a.tri + (size_t)w * d.ktri + (u0 * H - ((u0 * (u0 - 1)) >> 1) - u0);   // + v
             double* tri1 = tri0 + (H - u0 - 1);
-            for (int v = t; v < hp16; v += 16) {
-                const bool in = v < H;
-                const double2 o = lout[v < Q ? v : 0];
-                if (tri0) {          // packed triangle for the filter GEMM; the scratch copy only feeds the tap
-                    if (in && v >= u0) tri0[v] = o.x;
-                    if (in && has1 && v >= u1) tri1[v] = o.y;
-                    if (!a.convq) continue;
+            for (int v = t; v < H; v += 16) {
+                const double2 o = lout[v];
+                if (v >= u0) tri0[v] = o.x;
+                if (has1 && v >= u1) tri1[v] = o.y;
+                if (a.convq) {
+                    xc[(size_t)u0 * pitch + v] = o.x;
+                    if (has1) xc[(size_t)u1 * pitch + v] = o.y;
                 }
-                xc[(size_t)u0 * pitch + v] = in ? o.x : 0.0;
-                if (has1) xc[(size_t)u1 * pitch + v] = in ? o.y : 0.0;
             }
             __syncwarp(gmask);
         }
@@ -298,17 +296,7 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
             for (int i = tid; i < H * H; i += NT) cq[i] = xc[(size_t)(i / H) * pitch + (i % H)];
         }
 
-        // ---- D: G[kx] on the FP64 tensor cores, conv_c read from the scratch (L2); skipped when the filter GEMM follows
-        if (a.g) {
-            const int nsplit = k3_run_phase_d<0>(d, xc, pitch, gpart_s, warp, lane, NT / 32);
-            __syncthreads();
-            for (int k = tid; k < hp8; k += NT) {
-                double g = gpart_s[k];
-                for (int p = 1; p < nsplit; ++p) g += gpart_s[p * hp8 + k];
-                a.g[(size_t)w * hp8 + k] = g;
-            }
-        }
-        __syncthreads();       // phase D's reads of the scratch end before the next walker's synthesis overwrites it
+        __syncthreads();       // the tap's reads of the scratch end before the next walker's phases overwrite it
     }
 }
 
@@ -333,11 +321,10 @@ cudaError_t jx_szmap_large_configure(const jx_dev& d) {
 
 // scratch: [min(W, sm_count)][hp8][xs_pitch] doubles
 cudaError_t jx_launch_szmap_large(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
-                                  double* convq, double* g, double* tri, double* scratch, double* scratch2,
-                                  cudaStream_t st) {
+                                  double* convq, double* tri, double* scratch, double* scratch2, cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
     k3_args a;
-    a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.g = g; a.tri = tri; a.scratch = scratch; a.scratch2 = scratch2;
+    a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.tri = tri; a.scratch = scratch; a.scratch2 = scratch2;
     const int nt = k3l_pick_threads(d);
     const size_t smem = k3l_layout(d, nt).total;
     const int grid = W < sm_count ? W : sm_count;

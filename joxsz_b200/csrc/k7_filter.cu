@@ -52,18 +52,18 @@ JX_D void k7_dmma(double& c0, double& c1, double a, double b) {
 template <int NT>
 constexpr size_t k7_smem_bytes() { return (size_t)K7_STAGES * (K7_BM + 8 * NT) * K7_LDS * sizeof(double); }
 
-// A: [M, lda] packed convolved maps (lda = K rounded up to 32, zero padded), B: [8 NT, lda] = R^T zero padded,
-// C: [kparts][M][8 NT]
+// A: [M, lda] packed convolved maps (lda = K rounded up to 32, zero padded), B: [ldc, lda] = R^T zero padded,
+// C: [kparts][M][ldc]; blockIdx.z selects a block of 8 NT output columns (quarter planes wider than 136 pixels)
 template <int NT>
 __global__ void __launch_bounds__(K7_THREADS, 1)
-k7_filter_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int lda, int M,
-                      int nchunks_total, int chunks_per_part) {
+k7_filter_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int lda, int ldc,
+                      int M, int nchunks_total, int chunks_per_part) {
     extern __shared__ __align__(16) double k7_smem[];
     constexpr int BN = 8 * NT;
     double* As = k7_smem;                                          // [STAGES][BM][LDS]
     double* Bs = k7_smem + (size_t)K7_STAGES * K7_BM * K7_LDS;     // [STAGES][BN][LDS]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int part = blockIdx.x, m0 = blockIdx.y * K7_BM;
+    const int part = blockIdx.x, m0 = blockIdx.y * K7_BM, n0 = blockIdx.z * BN;
     const int c_first = part * chunks_per_part;
     const int nchunks = min(chunks_per_part, nchunks_total - c_first);
 
@@ -81,7 +81,7 @@ k7_filter_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B
             const int piece = it * K7_THREADS + tid;
             if (piece < BN * K7_BK / 2) {
                 const int row = piece >> 4, col = (piece & 15) * 2;
-                k7_cp16(Bs + ((size_t)stage * BN + row) * K7_LDS + col, B + (size_t)row * lda + k0 + col, true);
+                k7_cp16(Bs + ((size_t)stage * BN + row) * K7_LDS + col, B + (size_t)(n0 + row) * lda + k0 + col, true);
             }
         }
     };
@@ -121,14 +121,14 @@ k7_filter_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B
     k7_wait<0>();
 
     // lane owns C[row = lane / 4][col = 2 (lane % 4) + {0, 1}] of each 8 x 8 tile
-    double* Cp = C + (size_t)part * M * BN;
+    double* Cp = C + (size_t)part * M * ldc + n0;
 #pragma unroll
     for (int i = 0; i < K7_MT; ++i) {
         const int m = m0 + warp * (8 * K7_MT) + i * 8 + frow;
         if (m >= M) continue;
 #pragma unroll
         for (int j = 0; j < NT; ++j)
-            *reinterpret_cast<double2*>(Cp + (size_t)m * BN + j * 8 + 2 * fk) = make_double2(acc[i][j][0], acc[i][j][1]);
+            *reinterpret_cast<double2*>(Cp + (size_t)m * ldc + j * 8 + 2 * fk) = make_double2(acc[i][j][0], acc[i][j][1]);
     }
 }
 
@@ -136,12 +136,25 @@ k7_filter_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B
 
 }  // namespace
 
-// largest map quarter plane the kernel is instantiated for: 8 * 17 >= 129, the most a cyclic length of 256 admits
-bool jx_filter_supported(const jx_dev& d) { return d.hp8 / 8 >= 1 && d.hp8 / 8 <= 17; }
+// Output columns are handled in `nblk` blocks of 8 NT columns, NT <= 17 (register budget of the warp tile).
+void jx_filter_tiling(int hp8, int* nblk, int* nt) {
+    const int ntile = hp8 / 8;
+    *nblk = (ntile + 16) / 17;
+    *nt = (ntile + *nblk - 1) / *nblk;
+}
+
+// leading dimension of filt_op's rows-of-outputs and of the partial rows: 8 NT nblk >= hp8
+int jx_filter_pitch(int hp8) {
+    int nblk, nt;
+    jx_filter_tiling(hp8, &nblk, &nt);
+    return 8 * nt * nblk;
+}
 
 cudaError_t jx_filter_configure(const jx_dev& d) {
     const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    switch (d.hp8 / 8) {
+    int nblk, nt;
+    jx_filter_tiling(d.hp8, &nblk, &nt);
+    switch (nt) {
 #define K7_CASE(n) case n: return cudaFuncSetAttribute(k7_filter_gemm_kernel<n>, at, (int)k7_smem_bytes<n>());
         K7_FOR_NT(K7_CASE)
 #undef K7_CASE
@@ -149,23 +162,25 @@ cudaError_t jx_filter_configure(const jx_dev& d) {
     }
 }
 
-// Number of K parts: fixed by the geometry alone (JX_FILTER_CPP chunks of 32 per part), never by the batch size,
-// so that a walker's result does not depend on which batch it is evaluated in (the sampler's chains are
-// bit-identical for any number of ranks).  117 chunks -> 9 parts for the shipped cluster: 256 walker tiles x 9
-// parts fill 148 SMs to 97 %.
+// Number of K parts: fixed by the geometry alone, never by the batch size, so that a walker's result does not depend
+// on which batch it is evaluated in (the sampler's chains are bit-identical for any number of ranks): parts of
+// JX_FILTER_CPP chunks of 32, at most 9 parts (longer parts for the larger maps).  117 chunks -> 9 parts of 13 for
+// the shipped cluster: 256 walker tiles x 9 parts fill 148 SMs to 97 %.
 int jx_filter_parts(const jx_dev& d) {
-    const int nchunks = d.ktri / K7_BK;
-    return (nchunks + JX_FILTER_CPP - 1) / JX_FILTER_CPP;
+    const int nchunks = d.ktri / K7_BK, p = (nchunks + JX_FILTER_CPP - 1) / JX_FILTER_CPP;
+    return p < 9 ? p : 9;
 }
 
-// rowp[kparts][W][hp8] = partial sums of tri[W, ktri] . filt_op[hp8, ktri]^T
+// rowp[kparts][W][hpf] = partial sums of tri[W, ktri] . filt_op[hpf, ktri]^T
 cudaError_t jx_launch_filter(const jx_dev& d, const double* tri, int W, double* rowp, cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
-    const int nchunks = d.ktri / K7_BK, cpp = JX_FILTER_CPP;
-    dim3 grid(jx_filter_parts(d), (W + K7_BM - 1) / K7_BM);
-    switch (d.hp8 / 8) {
+    const int nchunks = d.ktri / K7_BK, parts = jx_filter_parts(d), cpp = (nchunks + parts - 1) / parts;
+    int nblk, nt;
+    jx_filter_tiling(d.hp8, &nblk, &nt);
+    dim3 grid(parts, (W + K7_BM - 1) / K7_BM, nblk);
+    switch (nt) {
 #define K7_CASE(n) case n: k7_filter_gemm_kernel<n><<<grid, K7_THREADS, k7_smem_bytes<n>(), st>>>( \
-                               tri, d.filt_op, rowp, d.ktri, W, nchunks, cpp); break;
+                               tri, d.filt_op, rowp, d.ktri, d.hpf, W, nchunks, cpp); break;
         K7_FOR_NT(K7_CASE)
 #undef K7_CASE
         default: return cudaErrorInvalidValue;

@@ -280,15 +280,12 @@ class PackedSetup:
         N, nr = self.N, self.nr
         pd = self.map_ops.P
         lg = math.log2
-        k7 = (self.H + 7) // 8 <= 17          # filter stage through the GEMM (k7_filter.cu): quarter plane up to 136 wide
         return {
             "project": 2.0 * nr * 4 * self.map_ops.nseg,
-            # filter stage: one GEMM row of K = H (H + 1) / 2 distinct convolved-map pixels by H outputs when the
-            # quarter plane fits the GEMM's tile (k7_filter.cu); otherwise the large-map kernel transforms all H rows
-            "filter": (2.0 * (self.H * (self.H + 1) // 2) * self.H if k7 else 2.0 * self.H ** 3),
-            # SURVEY 8(d) convention (full complex FFTs): padded convolution + exact-size filter.  The shared-memory
-            # map kernel (cyclic length 256) ends at the convolved map, so only the first half is its own
-            "szmap": (2 * 5 * pd * pd * lg(pd * pd) + 6 * pd * pd
-                      + (0 if k7 else 2 * 5 * N * N * lg(N * N) + 6 * N * N)),
+            # filter stage: one GEMM row of K = H (H + 1) / 2 distinct convolved-map pixels by H outputs (k7_filter.cu)
+            "filter": 2.0 * (self.H * (self.H + 1) // 2) * self.H,
+            # SURVEY 8(d) convention (full complex FFTs): padded convolution + exact-size filter.  The map kernels end
+            # at the convolved map, so only the first half is their own
+            "szmap": 2 * 5 * pd * pd * lg(pd * pd) + 6 * pd * pd,
             "szmap_plus_filter": 2 * 5 * pd * pd * lg(pd * pd) + 2 * 5 * N * N * lg(N * N) + 6 * pd * pd + 6 * N * N,
         }

@@ -45,16 +45,15 @@ def model_stages(pk, pp, direct_b=False):
         S = S * pk.bhat.T[None]                              # bhat[ky, kx]
         X2 = np.swapaxes(dct_even(S, P, H), 1, 2)            # [W, H(u), Q(kx)]   phase B inverse
     conv = dct_even(X2, P, H)                                # [W, H(u), H(v)]    phase C
-    if P == 256:
-        # shared-memory map kernel + K7: packed triangle u <= v of the convolved map times the filter-row operator
-        iu, iv = np.triu_indices(H)
-        tri = conv[:, iu, iv]                                # [W, H (H + 1) / 2], row-major packed
+    # K7: packed triangle u <= v of the convolved map times the filter-row operator
+    iu, iv = np.triu_indices(H)
+    tri = conv[:, iu, iv]                                    # [W, H (H + 1) / 2], row-major packed
+    if H <= 136:
         row = tri @ filter_row_operator(pk)                  # [W, v]
     else:
-        # large-map kernel: dense cosine transform of every row, reduced over ky, then the inverse of the row
-        C1 = conv @ pk.cmat                                  # [W, u, kx]         phase D
-        G = np.einsum("wuk,uk->wk", C1, pk.hf)
-        row = G @ pk.dinv                                    # [W, v]             phase E
+        # wide quarter planes: the same contraction without materialising the 32 896 x 256 operator in long double
+        C1 = conv @ pk.cmat                                  # [W, u, kx]
+        row = np.einsum("wuk,uk->wk", C1, pk.hf) @ pk.dinv   # [W, v]
     return dict(coef=coef, Z=Z, conv=conv, row=row)
 
 
