@@ -10,7 +10,8 @@
 // imaginary part) with no post-processing.  Per walker:
 //
 //   A  rows    Z[u,:]  (spline pieces evaluated on the fly)  --FFT256-->  xs[u, kx]      kx = 0..P/2
-//   B  columns xs[:, kx] --FFT256--> * bhat[ky, kx] --FFT256--> xs[u, kx]            (beam, cyclic length P)
+//   B  columns xs[:, kx]  (*) beam in (y offset, kx), 55 taps, directly           (small beams: the shipped case)
+//              or  xs[:, kx] --FFT256--> * bhat[ky, kx] --FFT256--> xs[u, kx]     (any beam, cyclic length P)
 //   C  rows    xs[u, :]  --FFT256--> conv_c[u, v]                = fftconvolve(y_2d, beam,'same')*step^2
 // and the kernel writes conv_c on u <= v (the convolved map is symmetric under x <-> y as well), packed row-major,
 // H (H + 1) / 2 doubles per walker, straight from the registers of phase C.  The remaining steps are batched over
@@ -18,7 +19,8 @@
 // transform) restricted to the consumed row is one DMMA GEMM with a constant operator (k7_filter.cu), then the
 // conversion / chi^2 tail (k5_tail.cu).
 // The per-walker inputs (spline coefficients) arrive by TMA bulk copy (cp.async.bulk + mbarrier),
-// double buffered against the previous walker's compute.
+// double buffered against the previous walker's compute; the per-thread constants of the walker loop
+// (synthesis-table entries, beam taps, FFT twiddles) sit in tensor memory (jx_tmem.cuh).
 #include "k3_common.cuh"
 #include "jx_tmem.cuh"
 #include <stdlib.h>
