@@ -98,12 +98,20 @@ JX_D void group_fft_even(int t, unsigned gmask, const double2* __restrict__ in, 
 constexpr int K3L_NB = JX_BMIX_ROWS, K3L_UB = 32;
 JX_D void k3l_yconv(const double* __restrict__ in, int pitch, int kx, int u0, int H, const double (&tap)[K3L_NB],
                     double (&acc)[K3L_UB]) {
+    constexpr int NIN = K3L_UB + 2 * (K3L_NB - 1), PF = 8;     // input rows; rows in flight ahead of the arithmetic
+    auto fetch = [&](int ii) {
+        const int up = u0 - (K3L_NB - 1) + ii, ua = up < 0 ? -up : up;
+        return ua < H ? in[(size_t)ua * pitch + kx] : 0.0;
+    };
 #pragma unroll
     for (int k = 0; k < K3L_UB; ++k) acc[k] = 0.0;
+    double xq[PF];
 #pragma unroll
-    for (int ii = 0; ii < K3L_UB + 2 * (K3L_NB - 1); ++ii) {
-        const int up = u0 - (K3L_NB - 1) + ii, ua = up < 0 ? -up : up;
-        const double x = ua < H ? in[(size_t)ua * pitch + kx] : 0.0;
+    for (int q = 0; q < PF; ++q) xq[q] = fetch(q);
+#pragma unroll
+    for (int ii = 0; ii < NIN; ++ii) {
+        const double x = xq[ii % PF];
+        if (ii + PF < NIN) xq[ii % PF] = fetch(ii + PF);
 #pragma unroll
         for (int k = 0; k < K3L_UB; ++k) {
             const int j = ii - (K3L_NB - 1) - k < 0 ? k + (K3L_NB - 1) - ii : ii - (K3L_NB - 1) - k;
@@ -184,14 +192,23 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
 
         // ---- A0: synthesise the quarter-plane map into the scratch (u <= v listed, mirrored on store)
         {
+            // eight table entries per thread in flight at a time (the table comes from L2)
             const int4* tab = reinterpret_cast<const int4*>(d.synth);
-            for (int i = tid; i < d.nsynth; i += NT) {
-                const int4 e = __ldg(tab + i);
-                const int sg = e.z & 0xffff, u = (e.z >> 16) & 0xffff, v = e.w & 0xffff;
-                if (u != 0xffff) {
-                    const double z = spline_eval(cf, d.nseg, sg, __hiloint2double(e.y, e.x));
-                    xs[(size_t)u * pitch + v] = z;
-                    xs[(size_t)v * pitch + u] = z;
+            for (int base = 0; base < d.nsynth; base += 8 * NT) {
+                int4 e[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = base + k * NT + tid;
+                    e[k] = i < d.nsynth ? __ldg(tab + i) : make_int4(0, 0, 0xffff0000, 0);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int sg = e[k].z & 0xffff, u = (e[k].z >> 16) & 0xffff, v = e[k].w & 0xffff;
+                    if (u != 0xffff) {
+                        const double z = spline_eval(cf, d.nseg, sg, __hiloint2double(e[k].y, e[k].x));
+                        xs[(size_t)u * pitch + v] = z;
+                        xs[(size_t)v * pitch + u] = z;
+                    }
                 }
             }
         }
@@ -202,13 +219,21 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
         for (int rp = grp; rp < npair; rp += ngroups) {
             const int u0 = 2 * rp, u1 = u0 + 1;
             const bool has1 = u1 < H;
-            for (int f = t; f < Q; f += 16) {
-                double2 v = make_double2(0.0, 0.0);
-                if (f < H) {
-                    v.x = xs[(size_t)u0 * pitch + f];
-                    if (has1) v.y = xs[(size_t)u1 * pitch + f];
+            {
+                constexpr int NL = (Q + 15) / 16;            // loads of the whole line in flight together (L2 latency)
+                double2 v[NL];
+#pragma unroll
+                for (int q = 0; q < NL; ++q) {
+                    const int f = t + 16 * q;
+                    v[q] = make_double2(0.0, 0.0);
+                    if (f < H) {
+                        v[q].x = xs[(size_t)u0 * pitch + f];
+                        if (has1) v[q].y = xs[(size_t)u1 * pitch + f];
+                    }
                 }
-                lin[f] = v;
+#pragma unroll
+                for (int q = 0; q < NL; ++q)
+                    if (t + 16 * q < Q) lin[t + 16 * q] = v[q];
             }
             __syncwarp(gmask);
             group_fft_even<R>(t, gmask, lin, lout, tw_s, twp_s, xbuf);
@@ -225,15 +250,23 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
         // columns dealt to the warps (about a quarter of the FP64 work of the two full-complex column FFTs, and no
         // staging through shared memory)
         if (bdirect) {
-            const int ncw = (Q + 31) >> 5, nrb = (H + K3L_UB - 1) / K3L_UB;
-            for (int task = warp; task < ncw * nrb; task += (NT >> 5)) {
-                const int cw = task % ncw, u0 = (task / ncw) * K3L_UB;
+            // tasks in column-group-major order, a contiguous share per warp: the taps of a column group are loaded
+            // once for the row blocks that follow each other
+            const int ncw = (Q + 31) >> 5, nrb = (H + K3L_UB - 1) / K3L_UB, ntask = ncw * nrb, nw = NT >> 5;
+            const int t_lo = (int)(((long)warp * ntask) / nw), t_hi = (int)(((long)(warp + 1) * ntask) / nw);
+            double tap[K3L_NB];
+            int cw_have = -1;
+            for (int task = t_lo; task < t_hi; ++task) {
+                const int cw = task / nrb, u0 = (task % nrb) * K3L_UB;
                 const int kx = 32 * cw + lane;
                 const bool on = kx < Q;
                 const int kxc = on ? kx : Q - 1;
-                double tap[K3L_NB], acc[K3L_UB];
+                if (cw != cw_have) {
 #pragma unroll
-                for (int j = 0; j < K3L_NB; ++j) tap[j] = __ldg(d.bmix + (size_t)j * d.bmix_pitch + kxc);
+                    for (int j = 0; j < K3L_NB; ++j) tap[j] = __ldg(d.bmix + (size_t)j * d.bmix_pitch + kxc);
+                    cw_have = cw;
+                }
+                double acc[K3L_UB];
                 k3l_yconv(xs, pitch, kxc, u0, H, tap, acc);
 #pragma unroll
                 for (int k = 0; k < K3L_UB; ++k)
@@ -270,8 +303,22 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
         for (int rp = grp; rp < npair; rp += ngroups) {
             const int u0 = 2 * rp, u1 = u0 + 1;
             const bool has1 = u1 < H;
-            for (int f = t; f < Q; f += 16)
-                lin[f] = make_double2(xc[(size_t)u0 * pitch + f], has1 ? xc[(size_t)u1 * pitch + f] : 0.0);
+            {
+                constexpr int NL = (Q + 15) / 16;
+                double2 v[NL];
+#pragma unroll
+                for (int q = 0; q < NL; ++q) {
+                    const int f = t + 16 * q;
+                    v[q] = make_double2(0.0, 0.0);
+                    if (f < Q) {
+                        v[q].x = xc[(size_t)u0 * pitch + f];
+                        if (has1) v[q].y = xc[(size_t)u1 * pitch + f];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < NL; ++q)
+                    if (t + 16 * q < Q) lin[t + 16 * q] = v[q];
+            }
             __syncwarp(gmask);
             group_fft_even<R>(t, gmask, lin, lout, tw_s, twp_s, xbuf);
             // conv_c[u, v] for v >= u goes to the packed triangle of this walker (row u starts at u H - u (u - 1) / 2);
