@@ -109,8 +109,10 @@ class BatchedLikelihood:
     #: small kernels and the launch count outweigh the hidden 0.7 ms of staging), hence the large value.
     HOST_CHUNK = 65536
 
-    def _call_host(self, a):
-        """numpy [W, ndim] -> numpy [W]: pinned staging, async H2D, kernels, async D2H, one synchronisation."""
+    def _call_host(self, a, pinned_src=None):
+        """numpy [W, ndim] -> numpy [W]: pinned staging, async H2D, kernels, async D2H, one synchronisation.
+        ``pinned_src``: the same data as a pinned float64 torch tensor (the caller's own page-locked buffer): the
+        staging copy is skipped and the host->device copy reads it directly."""
         W = a.shape[0]
         if a.shape[1] != self.ndim:
             raise ValueError(f"theta must be [W, {self.ndim}], got {a.shape}")
@@ -123,12 +125,15 @@ class BatchedLikelihood:
         if self._dev_in is None or self._dev_in.shape[0] < W:
             self._dev_in = self._new(max(W, 1), self.ndim)
             self._dev_out = self._new(max(W, 1))
-        src = torch.from_numpy(a)
+        src = torch.from_numpy(a) if pinned_src is None else pinned_src
         step = self.HOST_CHUNK if W > self.HOST_CHUNK else max(W, 1)
         for lo in range(0, W, step):
             hi = min(W, lo + step)
-            self._pinned_in[lo:hi].copy_(src[lo:hi])                       # host memcpy, overlaps the previous chunk
-            self._dev_in[lo:hi].copy_(self._pinned_in[lo:hi], non_blocking=True)
+            if pinned_src is None:
+                self._pinned_in[lo:hi].copy_(src[lo:hi])                   # host memcpy, overlaps the previous chunk
+                self._dev_in[lo:hi].copy_(self._pinned_in[lo:hi], non_blocking=True)
+            else:
+                self._dev_in[lo:hi].copy_(src[lo:hi], non_blocking=True)
             self.loglike_device(self._dev_in[lo:hi], out=self._dev_out[lo:hi])
             self._pinned_out[lo:hi].copy_(self._dev_out[lo:hi], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
@@ -141,6 +146,10 @@ class BatchedLikelihood:
         if was_torch and theta.is_cuda:
             ll = self.loglike_device(self._theta_dev(theta))
             return ll[0] if single else ll
+        if (was_torch and theta.dim() == 2 and theta.dtype == torch.float64 and theta.is_contiguous()
+                and theta.is_pinned()):
+            res = self._call_host(theta.numpy(), pinned_src=theta)     # page-locked input: no staging copy
+            return torch.from_numpy(res)
         a = theta.detach().numpy() if was_torch else np.asarray(theta)
         a = np.ascontiguousarray(np.atleast_2d(np.asarray(a, dtype=np.float64)))
         if a.ndim != 2:

@@ -226,3 +226,14 @@ def test_fft_form_of_the_beam_convolution(cl1226_fit, golden, engine, monkeypatc
     assert np.max(np.abs(ll_fft[ok] - ll[ok])) < 1e-9
     maps = engine.sz_maps(th[:2], want=("conv_2d",))["conv_2d"]
     assert rel_err_max(maps_fft, maps) < 1e-12
+
+
+def test_pinned_host_input(engine, golden):
+    """A page-locked float64 torch tensor is copied to the device directly (no staging copy) and gives the same
+    values as the numpy path; the result comes back as a host tensor."""
+    th = golden["thetas"]
+    ref = engine(th)
+    pinned = torch.from_numpy(np.ascontiguousarray(th)).pin_memory()
+    out = engine(pinned)
+    assert isinstance(out, torch.Tensor) and not out.is_cuda
+    assert np.array_equal(out.numpy(), ref)
