@@ -14,12 +14,12 @@ from helpers import oracle_setup_from_fit, orc, rel_err_max
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
-def _build(map_half, nr):
+def _build(map_half, nr, **overrides):
     from joxsz_b200 import cluster
     from joxsz_b200.mb import mb
     mb.fit.debugfit = False
     base = cluster.load_inputs_npz(os.path.join(ROOT, "tests", "golden", "cl1226_inputs.npz"))
-    inp = cluster.synthetic_inputs(map_half=map_half, nr=nr, base=base)
+    inp = cluster.synthetic_inputs(map_half=map_half, nr=nr, base=base, **overrides)
     fit, _ = cluster.build_fit(inp, savedir=None)
     return fit
 
@@ -47,12 +47,19 @@ def fit201():
     return _build(100, 320)
 
 
+# a beam wider than 55 pixels (FWHM 26"): no direct y convolution, the L2-staged kernel convolves through column FFTs;
+# the quarter plane (H > 136) also takes two column blocks in the filter GEMM
+@pytest.fixture(scope="module")
+def fitwide():
+    return _build(127, 512, beam_fwhm=26.0)
+
+
 def _draws(fit, n, seed, frac_bad=0.1):
     from joxsz_b200.synthetic import draw_parameters
     return draw_parameters(fit.thawed, n=n, seed=seed, spread=0.03, frac_bad=frac_bad)
 
 
-@pytest.mark.parametrize("which,P", [("fit141", 256), ("fit201", 256), ("fit255", 512), ("fit511", 1024)])
+@pytest.mark.parametrize("which,P", [("fit141", 256), ("fit201", 256), ("fit255", 512), ("fit511", 1024), ("fitwide", 512)])
 def test_tables_and_kernel_algorithm_on_cpu(which, P, request):
     """The packed tables + the kernel's sequence of operations (numpy model) reproduce the oracle's filtered row."""
     from joxsz_b200.packer import PackedSetup
@@ -73,7 +80,7 @@ def test_tables_and_kernel_algorithm_on_cpu(which, P, request):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which,nw", [("fit141", 48), ("fit201", 48), ("fit255", 48), ("fit511", 16)])
+@pytest.mark.parametrize("which,nw", [("fit141", 48), ("fit201", 48), ("fit255", 48), ("fit511", 16), ("fitwide", 32)])
 def test_large_map_loglike_matches_oracle(which, nw, request):
     from joxsz_b200.batched import BatchedLikelihood
     fit = request.getfixturevalue(which)
