@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define JX_ABI_VERSION 5
+#define JX_ABI_VERSION 6
 
 typedef enum jx_status {
     JX_OK = 0,
@@ -197,25 +197,31 @@ int jx_radial_profiles(const double* pars, int32_t W, int32_t dens_mode, const d
  * `inds = arange(n) % 2; shuffle(inds)`).  In the half-step `split` the active walkers are
  * perm[2 r + split], r = 0..ns-1 with ns = (nall - split + 1) / 2; a rank processes the contiguous slice
  * r in [r_first, r_first + r_count) -- equal, fixed-size work per rank whatever the colouring.
- * RNG: Philox4x32-10, key = seed, counter = (walker index, iteration, split | purpose): a chain does
- * not depend on the number of ranks.
+ * RNG: Philox4x32-10, key = seed, counter = (walker index, iteration lo, iteration hi, purpose | split << 2) with
+ * purpose 0 = proposal, 1 = acceptance, 2 = colouring keys: every draw of a walker in an iteration comes from its own
+ * Philox block, and a chain does not depend on the number of ranks.
+ * `iter_dev` (device pointer, may be NULL) is added to `iteration`: with the counter in device memory one sampler
+ * iteration can be captured in a CUDA graph and replayed (jx_stretch_advance increments the counter on the stream).
  *
  * propose: partner j = perm[2 rint + (1 - split)], rint uniform over the other colour;
  *          z = ((a-1) u + 1)^2 / a;  prop = c_j - (c_j - x_k) z;  factor = (ndim - 1) ln z. */
 int jx_stretch_propose(const double* coords, const int32_t* perm, int32_t nall, int32_t ndim, int32_t split,
                        int32_t r_first, int32_t r_count, double a, uint64_t seed, uint64_t iteration,
-                       double* prop /*[r_count,ndim]*/, double* factor /*[r_count]*/, int32_t device, void* stream);
+                       const uint64_t* iter_dev, double* prop /*[r_count,ndim]*/, double* factor /*[r_count]*/,
+                       int32_t device, void* stream);
 /* accept: packed[i] = (new position [ndim], new log-prob, accepted 0/1) for slice entry i, where the
  * move is accepted iff factor + lp_new - lp[k] > ln(u) (emcee RedBlueMove.propose). */
 int jx_stretch_accept(const double* coords, const double* lp, const int32_t* perm, int32_t nall, int32_t ndim,
                       int32_t split, int32_t r_first, int32_t r_count, const double* prop, const double* lp_new,
-                      const double* factor, uint64_t seed, uint64_t iteration,
+                      const double* factor, uint64_t seed, uint64_t iteration, const uint64_t* iter_dev,
                       double* packed /*[r_count, ndim+2]*/, int32_t device, void* stream);
 /* permutation: perm = argsort of 64 Philox bits per walker (stable), a uniformly random permutation that
  * depends only on (seed, iteration) -- identical on every rank, generated on the device.
  * Call with workspace == NULL to get the required size in *workspace_bytes. */
-int jx_stretch_permutation(int32_t* perm, int32_t nall, uint64_t seed, uint64_t iteration, void* workspace,
-                           size_t* workspace_bytes, int32_t device, void* stream);
+int jx_stretch_permutation(int32_t* perm, int32_t nall, uint64_t seed, uint64_t iteration, const uint64_t* iter_dev,
+                           void* workspace, size_t* workspace_bytes, int32_t device, void* stream);
+/* *iter_dev += by, in stream order (the last node of a captured sampler iteration). */
+int jx_stretch_advance(uint64_t* iter_dev, uint64_t by, int32_t device, void* stream);
 /* scatter: write the gathered results of all ranks, packed_all [>= ns, ndim+2] in r order, back into
  * coords / lp and add the acceptance flags to naccept [nall]. */
 int jx_stretch_scatter(double* coords, double* lp, int32_t* naccept, const int32_t* perm, int32_t nall,
@@ -228,10 +234,6 @@ enum jx_stage { JX_ST_PROFILES = 0, JX_ST_PROJECT, JX_ST_SZMAP, JX_ST_XRAY, JX_S
 int jx_set_profiling(jx_handle* h, int32_t on);
 /* Sum of per-stage device milliseconds and launch counts since the last reset [host outputs]; resets. */
 int jx_stage_times(jx_handle* h, double* ms /*[JX_NSTAGE]*/, int64_t* launches /*[JX_NSTAGE]*/);
-/* Sustained FP64 FMA throughput of the device in TFLOP/s (a dependent-chain-free DFMA loop). */
-int jx_measure_fp64_tflops(int32_t device, double* tflops);
-/* Sustained FP64 tensor-core (mma.sync.m8n8k4.f64, SASS DMMA) throughput in TFLOP/s. */
-int jx_measure_dmma_tflops(int32_t device, double* tflops);
 /* Library build info (arch, ABI). */
 const char* jx_build_info(void);
 

@@ -27,7 +27,9 @@ class BatchedLikelihood:
         self.lib = _lib.load()
         if device is None:
             device = torch.cuda.current_device()
-        self.device = torch.device("cuda", int(device) if not isinstance(device, torch.device) else device.index or 0)
+        if isinstance(device, torch.device):      # torch.device("cuda") has index None: that means the current device
+            device = device.index if device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", int(device))
         if packed is None:
             packed = PackedSetup(fit, max_walkers=max_walkers, device=self.device.index)
         else:

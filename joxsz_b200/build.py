@@ -61,5 +61,23 @@ def build(force=False, verbose=False):
     return LIB
 
 
+PEAKS_SRC = os.path.join(HERE, "..", "scripts", "jx_peaks.cu")
+PEAKS_LIB = os.path.join(HERE, "..", "scripts", "libjx_peaks.so")
+
+
+def build_peaks(force=False):
+    """Measurement tooling (FP64 FMA / DMMA peak microbenchmarks for bench.py): its own library under scripts/,
+    kept out of the product libjoxsz_b200.so."""
+    if not force and os.path.exists(PEAKS_LIB) and os.path.getmtime(PEAKS_LIB) >= os.path.getmtime(PEAKS_SRC):
+        return PEAKS_LIB
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+           "-shared", "-o", PEAKS_LIB, PEAKS_SRC, "-lcudart"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed on jx_peaks.cu:\n{r.stdout}")
+    return PEAKS_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_peaks(force="--force" in sys.argv))

@@ -95,7 +95,7 @@ void flush_stage_events(jx_handle* h) {
 }  // namespace
 
 extern "C" const char* jx_build_info(void) {
-    return "libjoxsz_b200 abi=" "5" " arch=sm_100a fp64 K1=profiles K2=dmma-project K3=fft256-szmap(smem)|fft512/1024-szmap(L2) K7=dmma-filter K4=xray K5=tail";
+    return "libjoxsz_b200 abi=" "6" " arch=sm_100a fp64 K1=profiles K2=dmma-project K3=fft256-szmap(smem)|fft512/1024-szmap(L2) K7=dmma-filter K4=xray K5=tail";
 }
 
 extern "C" const char* jx_last_error(const jx_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -476,8 +476,8 @@ extern "C" int jx_loglike(jx_handle* h, const double* theta, int32_t W, double* 
     if (prof) JX_CUDA(h, cudaEventRecord(h->ev[1], st));
     // The X-ray kernel (latency bound, a few registers) only depends on the profiles: it runs on the handle's side
     // stream and shares the SMs with the projection GEMM.  It may set the "profile not > 0" bit of a walker while
-    // the map kernel reads the status word to decide whether to skip that walker: either way the tail kernel,
-    // after the join, writes -inf for it.
+    // the map kernel runs: the map kernel masks that bit out of its skip test (its decision only uses the bits the
+    // profile kernel wrote, which are final), and the tail kernel, after the join, writes -inf for the walker.
     JX_CUDA(h, cudaEventRecord(h->ev_fork, st));
     JX_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
     if (prof) JX_CUDA(h, cudaEventRecord(h->evx[0], h->side));
@@ -631,96 +631,4 @@ extern "C" int jx_stage_times(jx_handle* h, double* ms, int64_t* launches) {
         h->stage_launches[i] = 0;
     }
     return JX_OK;
-}
-
-namespace {
-__global__ void fp64_peak_kernel(double* out, int iters) {
-    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
-           a7 = a0 + 7;
-    const double m = 1.0000001, c = 1e-7;
-    for (int i = 0; i < iters; ++i) {
-        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
-}
-__global__ void dmma_peak_kernel(double* out, int iters) {
-    double c[8][2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
-    const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
-    }
-    double s = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-}  // namespace
-
-extern "C" int jx_measure_dmma_tflops(int32_t device, double* tflops) {
-    if (!tflops) return JX_ERR_INVALID;
-    if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return JX_ERR_CUDA;
-    const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 1 << 12;
-    double* buf = nullptr;
-    if (cudaMalloc(&buf, sizeof(double) * blocks * threads) != cudaSuccess) return JX_ERR_CUDA;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    dmma_peak_kernel<<<blocks, threads>>>(buf, iters);   // warm-up
-    double best = 0.0;
-    for (int rep = 0; rep < 5; ++rep) {
-        cudaEventRecord(e0);
-        dmma_peak_kernel<<<blocks, threads>>>(buf, iters);
-        cudaEventRecord(e1);
-        cudaEventSynchronize(e1);
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
-        // one m8n8k4 = 8*8*4 FMA = 512 flop per warp
-        double tf = 512.0 * 8.0 * (double)iters * blocks * (threads / 32) / (ms * 1e-3) / 1e12;
-        if (tf > best) best = tf;
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(buf);
-    cudaError_t e = cudaGetLastError();
-    *tflops = best;
-    return e == cudaSuccess ? JX_OK : JX_ERR_CUDA;
-}
-
-extern "C" int jx_measure_fp64_tflops(int32_t device, double* tflops) {
-    if (!tflops) return JX_ERR_INVALID;
-    if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return JX_ERR_CUDA;
-    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
-    double* buf = nullptr;
-    if (cudaMalloc(&buf, sizeof(double) * blocks * threads) != cudaSuccess) return JX_ERR_CUDA;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    fp64_peak_kernel<<<blocks, threads>>>(buf, iters);   // warm-up
-    double best = 0.0;
-    for (int rep = 0; rep < 5; ++rep) {
-        cudaEventRecord(e0);
-        fp64_peak_kernel<<<blocks, threads>>>(buf, iters);
-        cudaEventRecord(e1);
-        cudaEventSynchronize(e1);
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
-        double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
-        if (tf > best) best = tf;
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(buf);
-    cudaError_t e = cudaGetLastError();
-    *tflops = best;
-    return e == cudaSuccess ? JX_OK : JX_ERR_CUDA;
 }

@@ -166,8 +166,12 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
     }
 
     int it = 0;
-    // status bits of the walker one iteration ahead, so that the load is never waited for
-    uint32_t flag_next = (a.flags && w_first < a.W) ? a.flags[w_first] : 0u;
+    // status bits of the walker one iteration ahead, so that the load is never waited for.  Only the bits the profile
+    // kernel wrote (final before this kernel starts) decide the skip: the X-ray kernel may still be OR-ing
+    // JX_FLAG_XNONPOS into the word on the side stream, and a bit that changes under the readers would make the
+    // decision differ between the warps of a CTA (mismatched barriers).  The tail kernel sees every bit.
+    constexpr uint32_t K3_SKIP_BITS = ~(uint32_t)JX_FLAG_XNONPOS;
+    uint32_t flag_next = (a.flags && w_first < a.W) ? (a.flags[w_first] & K3_SKIP_BITS) : 0u;
     for (int w = w_first; w < a.W; w += gridDim.x, ++it) {
         const int buf = it & 1;
         const double* cf = coef_s + (size_t)buf * d.ncoef;
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(NT, 1) k3_szmap_kernel(const __grid_constant__
         const bool skip = flag_next != 0u;
         {
             const int wn = w + gridDim.x;
-            flag_next = (a.flags && wn < a.W) ? a.flags[wn] : 0u;
+            flag_next = (a.flags && wn < a.W) ? (a.flags[wn] & K3_SKIP_BITS) : 0u;
         }
         mbar_wait(&mbar[buf], (uint32_t)((it >> 1) & 1));
         if (skip) {                         // block-uniform: the tail kernel writes -inf for flagged walkers

@@ -183,7 +183,9 @@ __global__ void __launch_bounds__(256, 1) k3l_szmap_kernel(const __grid_constant
                              &mbar[buf ^ 1]);
             }
         }
-        const bool skip = a.flags && a.flags[w] != 0u;
+        // only the bits the profile kernel wrote decide the skip: JX_FLAG_XNONPOS may still be arriving from the
+        // X-ray kernel on the side stream and must not split the CTA's control flow (see k3_szmap.cu)
+        const bool skip = a.flags && (a.flags[w] & ~(uint32_t)JX_FLAG_XNONPOS) != 0u;
         mbar_wait(&mbar[buf], (uint32_t)((it >> 1) & 1));
         if (skip) {
             __syncthreads();

@@ -4,8 +4,11 @@
 // of RedBlueMove.propose (emcee 3.x; driven by the reference at joxsz_funcs.py:593-622 through
 // EnsembleSampler, joxsz_main.py:206-210).  The likelihood of the proposals is evaluated in between
 // by jx_loglike.  Random numbers come from Philox4x32-10 keyed by the run seed with the counter
-// (global walker index, iteration, split | purpose), so a chain is bit-identical however the
-// ensemble is sharded over GPUs.
+// (global walker index, iteration, purpose | split << 2), so a chain is bit-identical however the
+// ensemble is sharded over GPUs.  Every (purpose, split) pair has its own counter word: the shuffle keys, the
+// proposal draws and the acceptance draws of a walker in one iteration are independent Philox blocks.
+// The iteration every kernel uses is `iteration + *iter_dev` (iter_dev may be NULL): with the counter in device
+// memory a whole sampler iteration is one CUDA graph that is replayed unchanged (jx_stretch_advance bumps it).
 #include <cub/device/device_radix_sort.cuh>
 
 #include "jx_common.cuh"
@@ -36,15 +39,21 @@ JX_HD double u01(uint32_t hi, uint32_t lo) {       // 53-bit uniform in [0, 1)
 }
 
 constexpr uint32_t PURPOSE_PROPOSE = 0u, PURPOSE_ACCEPT = 1u, PURPOSE_SHUFFLE = 2u;
+JX_HD uint32_t stream_word(uint32_t purpose, int split) { return purpose | ((uint32_t)split << 2); }
+JX_D uint64_t effective_iteration(uint64_t iteration, const uint64_t* iter_dev) {
+    return iter_dev ? iteration + *iter_dev : iteration;
+}
 
 __global__ void k6_propose_kernel(const double* __restrict__ coords, const int32_t* __restrict__ perm, int nall,
                                   int ndim, int split, int r_first, int r_count, double a, uint64_t seed,
-                                  uint64_t iteration, double* __restrict__ prop, double* __restrict__ factor) {
+                                  uint64_t iteration, const uint64_t* __restrict__ iter_dev,
+                                  double* __restrict__ prop, double* __restrict__ factor) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= r_count) return;
+    iteration = effective_iteration(iteration, iter_dev);
     const int k = perm[2 * (r_first + i) + split];
     philox4 r = philox4x32_10((uint32_t)k, (uint32_t)iteration, (uint32_t)(iteration >> 32),
-                              ((uint32_t)split << 1) | PURPOSE_PROPOSE, (uint32_t)seed, (uint32_t)(seed >> 32));
+                              stream_word(PURPOSE_PROPOSE, split), (uint32_t)seed, (uint32_t)(seed >> 32));
     const double u = u01(r.v[0], r.v[1]);
     const double root = (a - 1.0) * u + 1.0;
     const double z = root * root / a;
@@ -62,12 +71,13 @@ __global__ void k6_accept_kernel(const double* __restrict__ coords, const double
                                  const int32_t* __restrict__ perm, int ndim, int split, int r_first, int r_count,
                                  const double* __restrict__ prop, const double* __restrict__ lp_new,
                                  const double* __restrict__ factor, uint64_t seed, uint64_t iteration,
-                                 double* __restrict__ packed) {
+                                 const uint64_t* __restrict__ iter_dev, double* __restrict__ packed) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= r_count) return;
+    iteration = effective_iteration(iteration, iter_dev);
     const int k = perm[2 * (r_first + i) + split];
     philox4 r = philox4x32_10((uint32_t)k, (uint32_t)iteration, (uint32_t)(iteration >> 32),
-                              ((uint32_t)split << 1) | PURPOSE_ACCEPT, (uint32_t)seed, (uint32_t)(seed >> 32));
+                              stream_word(PURPOSE_ACCEPT, split), (uint32_t)seed, (uint32_t)(seed >> 32));
     const double lnu = log(u01(r.v[0], r.v[1]));
     const double lnpdiff = factor[i] + lp_new[i] - lp[k];
     const bool acc = lnpdiff > lnu;
@@ -92,21 +102,25 @@ __global__ void k6_scatter_kernel(double* __restrict__ coords, double* __restric
 
 // sort keys of the colouring permutation: 64 random bits per walker (ties are broken by the stable sort)
 __global__ void k6_shuffle_keys_kernel(uint64_t* __restrict__ keys, int32_t* __restrict__ vals, int nall, uint64_t seed,
-                                       uint64_t iteration) {
+                                       uint64_t iteration, const uint64_t* __restrict__ iter_dev) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nall) return;
-    philox4 r = philox4x32_10((uint32_t)i, (uint32_t)iteration, (uint32_t)(iteration >> 32), PURPOSE_SHUFFLE,
-                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    iteration = effective_iteration(iteration, iter_dev);
+    philox4 r = philox4x32_10((uint32_t)i, (uint32_t)iteration, (uint32_t)(iteration >> 32),
+                              stream_word(PURPOSE_SHUFFLE, 0), (uint32_t)seed, (uint32_t)(seed >> 32));
     keys[i] = ((uint64_t)r.v[0] << 32) | r.v[1];
     vals[i] = i;
 }
+
+__global__ void k6_advance_kernel(uint64_t* iter_dev, uint64_t by) { *iter_dev += by; }
 
 }  // namespace
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
-extern "C" int jx_stretch_permutation(int32_t* perm, int32_t nall, uint64_t seed, uint64_t iteration, void* workspace,
-                                      size_t* workspace_bytes, int32_t device, void* stream) {
+extern "C" int jx_stretch_permutation(int32_t* perm, int32_t nall, uint64_t seed, uint64_t iteration,
+                                      const uint64_t* iter_dev, void* workspace, size_t* workspace_bytes,
+                                      int32_t device, void* stream) {
     if (nall < 1 || !workspace_bytes) return JX_ERR_INVALID;
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
@@ -125,7 +139,7 @@ extern "C" int jx_stretch_permutation(int32_t* perm, int32_t nall, uint64_t seed
     uint64_t* keys_out = (uint64_t*)(base + kb);
     int32_t* vals_in = (int32_t*)(base + 2 * kb);
     void* tmp = base + 2 * kb + vb;
-    k6_shuffle_keys_kernel<<<(nall + 255) / 256, 256, 0, st>>>(keys_in, vals_in, nall, seed, iteration);
+    k6_shuffle_keys_kernel<<<(nall + 255) / 256, 256, 0, st>>>(keys_in, vals_in, nall, seed, iteration, iter_dev);
     if (cub::DeviceRadixSort::SortPairs(tmp, cub_bytes, keys_in, keys_out, vals_in, perm, nall, 0, 64, st) != cudaSuccess)
         return JX_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? JX_OK : JX_ERR_CUDA;
@@ -139,26 +153,27 @@ static bool slice_ok(int nall, int split, int r_first, int r_count) {
 
 extern "C" int jx_stretch_propose(const double* coords, const int32_t* perm, int32_t nall, int32_t ndim,
                                   int32_t split, int32_t r_first, int32_t r_count, double a, uint64_t seed,
-                                  uint64_t iteration, double* prop, double* factor, int32_t device, void* stream) {
+                                  uint64_t iteration, const uint64_t* iter_dev, double* prop, double* factor,
+                                  int32_t device, void* stream) {
     if (!coords || !perm || !prop || !factor || ndim < 1 || !(a > 1.0)) return JX_ERR_INVALID;
     if (!slice_ok(nall, split, r_first, r_count)) return JX_ERR_INVALID;
     if (r_count == 0) return JX_OK;
     if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
     k6_propose_kernel<<<(r_count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        coords, perm, nall, ndim, split, r_first, r_count, a, seed, iteration, prop, factor);
+        coords, perm, nall, ndim, split, r_first, r_count, a, seed, iteration, iter_dev, prop, factor);
     return cudaGetLastError() == cudaSuccess ? JX_OK : JX_ERR_CUDA;
 }
 
 extern "C" int jx_stretch_accept(const double* coords, const double* lp, const int32_t* perm, int32_t nall,
                                  int32_t ndim, int32_t split, int32_t r_first, int32_t r_count, const double* prop,
                                  const double* lp_new, const double* factor, uint64_t seed, uint64_t iteration,
-                                 double* packed, int32_t device, void* stream) {
+                                 const uint64_t* iter_dev, double* packed, int32_t device, void* stream) {
     if (!coords || !lp || !perm || !prop || !lp_new || !factor || !packed || ndim < 1) return JX_ERR_INVALID;
     if (!slice_ok(nall, split, r_first, r_count)) return JX_ERR_INVALID;
     if (r_count == 0) return JX_OK;
     if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
     k6_accept_kernel<<<(r_count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        coords, lp, perm, ndim, split, r_first, r_count, prop, lp_new, factor, seed, iteration, packed);
+        coords, lp, perm, ndim, split, r_first, r_count, prop, lp_new, factor, seed, iteration, iter_dev, packed);
     return cudaGetLastError() == cudaSuccess ? JX_OK : JX_ERR_CUDA;
 }
 
@@ -171,5 +186,12 @@ extern "C" int jx_stretch_scatter(double* coords, double* lp, int32_t* naccept, 
     if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
     k6_scatter_kernel<<<(ns + 127) / 128, 128, 0, (cudaStream_t)stream>>>(coords, lp, naccept, perm, ndim, split,
                                                                             packed_all, ns);
+    return cudaGetLastError() == cudaSuccess ? JX_OK : JX_ERR_CUDA;
+}
+
+extern "C" int jx_stretch_advance(uint64_t* iter_dev, uint64_t by, int32_t device, void* stream) {
+    if (!iter_dev) return JX_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
+    k6_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(iter_dev, by);
     return cudaGetLastError() == cudaSuccess ? JX_OK : JX_ERR_CUDA;
 }

@@ -18,7 +18,20 @@ from .mb import mb
 # engine cache: one BatchedLikelihood per fit object, rebuilt when the frozen set-up changes
 # ----------------------------------------------------------------------------------------------
 
+def _arr_id(a):
+    """Cheap identity of a data array: a replaced or reshaped array changes it (in-place edits do not: call
+    :func:`jx_invalidate` after those)."""
+    if a is None:
+        return None
+    try:
+        return (id(a), tuple(np.shape(a)))
+    except Exception:
+        return id(a)
+
+
 def _signature(fit):
+    """Everything the device engine bakes in at ``jx_create``: thawed names, priors, frozen values, N_H, the density
+    mode and the identity of every data array (SZ data, beam, filter, grids, bands, count-rate tables)."""
     sz = fit.data.sz
     sig = [tuple(fit.thawed), bool(getattr(fit, "exclude_unphy_mass", False)),
            (bool(getattr(sz, "calc_integ", False)), getattr(sz, "integ_mu", None), getattr(sz, "integ_sig", None))]
@@ -30,22 +43,64 @@ def _signature(fit):
                 sig.append((name, "b", float(par.minval), float(par.maxval)))
         else:
             sig.append((name, "f", float(np.asarray(par.val).reshape(-1)[0])))
+    model = getattr(fit, "model", None)
+    sig.append(("NH", float(getattr(model, "NH_1022pcm2", 0.0) or 0.0)))
+    sig.append(("dens", getattr(getattr(model, "ne_cmpt", None), "mode", None)))
+    for k in ("flux_data", "beam_2d", "filtering", "r_pp", "radius", "d_mat", "convert"):
+        sig.append((k, _arr_id(getattr(sz, k, None))))
+    sig.append(("step", getattr(sz, "step", None), getattr(sz, "kpc_as", None), getattr(sz, "sep", None)))
+    bands = getattr(fit.data, "bands", None) or ()
+    for b in bands:
+        sig.append(("band", _arr_id(getattr(b, "cts", None)), _arr_id(getattr(b, "exposures", None)),
+                    _arr_id(getattr(b, "backrates", None)), _arr_id(getattr(b, "areascales", None))))
+    ctr = getattr(getattr(fit.data, "annuli", None), "ctrate", None)
+    cache = getattr(ctr, "ctcache", None)
+    if cache is not None:
+        sig.append(("ctcache", id(cache), len(cache)))
     return tuple(sig)
+
+
+# The engine holds ctypes pointers and device memory: it must not live in ``fit.__dict__`` -- the reference pickles the
+# fit right after ``doFitting`` (``joxsz_main.py:193-194``) and emcee pickles ``fit.getLikelihood`` for its pool.
+# Engines are kept here, keyed by the identity of the fit object and dropped when the fit is collected.
+_ENGINES = {}
+
+
+def _drop_engine(key):
+    ent = _ENGINES.pop(key, None)
+    if ent is not None:
+        try:
+            ent[1].close()
+        except Exception:
+            pass
+
+
+def jx_invalidate(fit):
+    """Forget the device engine of ``fit`` (call after editing one of its data arrays in place)."""
+    _drop_engine(id(fit))
 
 
 def engine_for(fit, min_walkers=1):
     """The fit's :class:`BatchedLikelihood`, (re)built on demand."""
+    import weakref
     from .batched import BatchedLikelihood
-    eng = fit.__dict__.get("_jx_engine")
+    key = id(fit)
+    ent = _ENGINES.get(key)
+    if ent is not None and ent[0]() is not fit:          # a dead object's id was reused
+        _drop_engine(key)
+        ent = None
     sig = _signature(fit)
-    if eng is not None and fit.__dict__.get("_jx_sig") == sig and eng.max_walkers >= min_walkers:
-        return eng
-    if eng is not None:
-        eng.close()
+    if ent is not None and ent[2] == sig and ent[1].max_walkers >= min_walkers:
+        return ent[1]
+    if ent is not None:
+        _drop_engine(key)
     cap = max(int(min_walkers), int(getattr(fit, "jx_max_walkers", 1024)))
     eng = BatchedLikelihood(fit, max_walkers=cap)
-    fit.__dict__["_jx_engine"] = eng
-    fit.__dict__["_jx_sig"] = sig
+    try:
+        ref = weakref.ref(fit, lambda _r, k=key: _drop_engine(k))
+    except TypeError:                                    # not weak-referenceable: keep it alive with the engine
+        ref = (lambda f: (lambda: f))(fit)
+    _ENGINES[key] = (ref, eng, sig)
     return eng
 
 

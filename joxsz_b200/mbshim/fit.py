@@ -12,6 +12,26 @@ class Fit:
         self.refreshThawed()
         self.bestlike = -1e99
 
+    # Methods bound on the INSTANCE (joxsz_b200.cluster.build_fit does that so that several fits can live in one
+    # process; the reference binds on the class) refer back to the object: pickle would resolve them with getattr on
+    # the half-built copy.  They travel as plain functions and are re-bound on the copy.
+    def __getstate__(self):
+        from types import MethodType
+        d = dict(self.__dict__)
+        bound = {k: v.__func__ for k, v in d.items() if isinstance(v, MethodType) and v.__self__ is self}
+        for k in bound:
+            del d[k]
+        d["__bound__"] = bound
+        return d
+
+    def __setstate__(self, d):
+        from types import MethodType
+        d = dict(d)
+        bound = d.pop("__bound__", {})
+        self.__dict__.update(d)
+        for k, f in bound.items():
+            setattr(self, k, MethodType(f, self))
+
     def refreshThawed(self):
         self.thawed = [name for name, par in sorted(self.pars.items()) if not par.frozen]
 

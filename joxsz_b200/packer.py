@@ -172,7 +172,15 @@ class PackedSetup:
         self.N, self.H, self.sep, self.nr = N, H, sep, nr
         # optional integrated-Compton-parameter penalty (joxsz_funcs.py:480-487)
         self.calc_integ = bool(getattr(sz, "calc_integ", False))
-        self.w_integ = _f64(self.y_op.T @ integ_weights(r_pp, float(sz.kpc_as), float(sz.step)))
+        # the reference only forms the integration grid when calc_integ is on (joxsz_funcs.py:480): a setup whose
+        # floating-point arange grid is one sample off must still pack when the penalty is disabled
+        if self.calc_integ:
+            self.w_integ = _f64(self.y_op.T @ integ_weights(r_pp, float(sz.kpc_as), float(sz.step)))
+        else:
+            try:
+                self.w_integ = _f64(self.y_op.T @ integ_weights(r_pp, float(sz.kpc_as), float(sz.step)))
+            except PackError:
+                self.w_integ = np.zeros(nr, dtype=np.float64)      # the 'integ' tap then reads 0
         self.integ_mu = float(sz.integ_mu) if getattr(sz, "integ_mu", None) is not None else 0.0
         self.integ_sig = float(sz.integ_sig) if getattr(sz, "integ_sig", None) is not None else 1.0
         if self.calc_integ and not (self.integ_sig > 0 and math.isfinite(self.integ_mu)):

@@ -44,8 +44,16 @@ class CudaStretchOps:
         self.lib = _lib.load()
         self.device = device
         self.index = device.index if device.index is not None else torch.cuda.current_device()
-        self._ws = None
-        self._ws_n = self._ws_bytes = 0
+        self._ws = {}
+        #: when set (a [1] int64 CUDA tensor), every kernel adds ``*iter_dev`` to the ``iteration`` it is given:
+        #: the sampler captures an iteration in a CUDA graph with ``iteration`` = 0 / 1 and the counter on the device
+        self.iter_dev = None
+
+    def _iter_ptr(self):
+        return _ptr(self.iter_dev)
+
+    def advance(self, by=1):
+        _lib.check(self.lib.jx_stretch_advance(_ptr(self.iter_dev), C.c_uint64(by), self.index, self._stream()))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -53,29 +61,33 @@ class CudaStretchOps:
     def permutation(self, perm, seed, iteration):
         """Colouring permutation of this iteration, generated on the device (identical on every rank)."""
         nall = perm.shape[0]
-        if self._ws is None or self._ws_n != nall:
+        # one sort workspace per destination buffer: the permutations of two consecutive iterations are produced
+        # on different streams (and, in graph mode, by different graphs) and may overlap in time
+        key = (nall, perm.data_ptr())
+        ws = self._ws.get(key)
+        if ws is None:
             need = C.c_size_t(0)
-            _lib.check(self.lib.jx_stretch_permutation(None, nall, C.c_uint64(0), C.c_uint64(0), None,
+            _lib.check(self.lib.jx_stretch_permutation(None, nall, C.c_uint64(0), C.c_uint64(0), None, None,
                                                        C.byref(need), self.index, None))
-            self._ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
-            self._ws_n, self._ws_bytes = nall, need.value
-        nbytes = C.c_size_t(self._ws_bytes)
+            ws = self._ws[key] = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+        nbytes = C.c_size_t(ws.numel())
         rc = self.lib.jx_stretch_permutation(_ptr(perm), nall, C.c_uint64(seed), C.c_uint64(iteration),
-                                             _ptr(self._ws), C.byref(nbytes), self.index, self._stream())
+                                             self._iter_ptr(), _ptr(ws), C.byref(nbytes), self.index, self._stream())
         _lib.check(rc)
 
     def propose(self, coords, perm, split, r_first, r_count, a, seed, iteration, prop, factor):
         nall, ndim = coords.shape
         rc = self.lib.jx_stretch_propose(_ptr(coords), _ptr(perm), nall, ndim, split, r_first, r_count, float(a),
-                                         C.c_uint64(seed), C.c_uint64(iteration), _ptr(prop), _ptr(factor),
-                                         self.index, self._stream())
+                                         C.c_uint64(seed), C.c_uint64(iteration), self._iter_ptr(), _ptr(prop),
+                                         _ptr(factor), self.index, self._stream())
         _lib.check(rc)
 
     def accept(self, coords, lp, perm, split, r_first, r_count, prop, lp_new, factor, seed, iteration, packed):
         nall, ndim = coords.shape
         rc = self.lib.jx_stretch_accept(_ptr(coords), _ptr(lp), _ptr(perm), nall, ndim, split, r_first, r_count,
                                         _ptr(prop), _ptr(lp_new), _ptr(factor), C.c_uint64(seed),
-                                        C.c_uint64(iteration), _ptr(packed), self.index, self._stream())
+                                        C.c_uint64(iteration), self._iter_ptr(), _ptr(packed), self.index,
+                                        self._stream())
         _lib.check(rc)
 
     def scatter(self, coords, lp, naccept, perm, split, packed_all, ns):
@@ -129,7 +141,7 @@ class EnsembleSampler:
     """
 
     def __init__(self, nwalkers, ndim, log_prob_fn, pool=None, backend=None, a=2.0, seed=None, world_size=1,
-                 rank=0, group=None, ops=None, device=None, vectorize=True, moves=None):
+                 rank=0, group=None, ops=None, device=None, vectorize=True, moves=None, graph=None):
         if nwalkers < 2 * ndim:
             raise ValueError("The number of walkers needs to be at least twice the dimension of the problem")
         if moves is not None:
@@ -159,10 +171,20 @@ class EnsembleSampler:
         if self.device is None:
             raise ValueError("device unknown")
         self.ops = ops if ops is not None else CudaStretchOps(self.device)
+        #: one ensemble iteration as ONE CUDA graph launch (the ~20 kernel launches, the side-stream fork/joins and the
+        #: all-gathers of an iteration are replayed by the driver instead of being issued from Python one by one).
+        #: None = on whenever the kernels are the CUDA ones; the first GRAPH_EAGER_STEPS iterations always run eagerly
+        #: (they warm up NCCL and the allocator), then the iteration is captured once and replayed.
+        self.use_graph = isinstance(self.ops, CudaStretchOps) if graph is None else bool(graph)
+        if self.use_graph and not isinstance(self.ops, CudaStretchOps):
+            raise ValueError("graph=True needs the CUDA stretch-move kernels")
+        self._graph = None
+        self._graph_failed = None
         self.initspread = 0.1
         self.pos0 = None
         self.backend = self                   # mcmc.backend.get_chain()/get_log_prob()/reset(...)
         self.iteration = 0                    # global Philox counter: never reset, so restarts do not repeat draws
+        self._steps_total = 0                 # steps since construction (reset() does not clear it)
         self.aux_launches = 0
         self._coords = self._lp = None
         self._chain = self._chain_lp = None
@@ -193,6 +215,17 @@ class EnsembleSampler:
             self._perm_ready = [torch.cuda.Event(), torch.cuda.Event()]
             self._step_done = torch.cuda.Event()
         self._steps_done = 0
+        # graph mode: iteration counter of the Philox streams in device memory, the permutation the graph reads and the
+        # one its side branch produces for the next iteration, re-pack buffer of odd ensembles
+        self._iter_dev = self._perm_g = self._perm_next = None
+        self._iter_dev_value = None
+        self._pa_buf = None
+        if self.world > 1:
+            self._pa_buf = torch.zeros((per * self.world, nd + 2), dtype=f64, device=dev)
+        if self.use_graph:
+            self._iter_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
+            self._perm_g = torch.zeros((W,), dtype=torch.int32, device=dev)
+            self._perm_next = torch.zeros((W,), dtype=torch.int32, device=dev)
 
     def _all_gather(self, out, inp):
         import torch.distributed as dist
@@ -239,9 +272,35 @@ class EnsembleSampler:
         return self.per0
 
     # ------------------------------------------------------------------ one ensemble iteration
-    def step(self):
-        """One stretch-move iteration: two half-steps, every walker proposed and evaluated once."""
+    GRAPH_EAGER_STEPS = 2
+
+    def _half_steps(self, perm, it):
+        """The two half-steps of an iteration on the current stream (``it``: the iteration the kernels are given; in
+        graph mode they add the device-side counter to it)."""
         W = self.nwalkers
+        for split in (0, 1):
+            ns = (W - split + 1) // 2
+            per, first, count = shard_bounds(ns, self.world, self.rank)
+            if count:
+                prop = self._prop[:count]
+                self.ops.propose(self._coords, perm, split, first, count, self.a, self.seed, it, prop, self._factor)
+                self.engine.loglike_device(prop, out=self._lpnew[:count])
+                self.ops.accept(self._coords, self._lp, perm, split, first, count, prop, self._lpnew,
+                                self._factor, self.seed, it, self._packed)
+            if self.world > 1:
+                # static shape [per0, ndim+2] per rank; rows beyond `ns` are never read by scatter
+                self._all_gather(self._packed_all, self._packed)
+                if per != self.per0:       # odd ensembles: the second colour has one walker fewer -> re-pack rows
+                    pa = self._pa_buf[:self.world * per]
+                    pa.view(self.world, per, -1).copy_(self._packed_all.view(self.world, self.per0, -1)[:, :per])
+                else:
+                    pa = self._packed_all
+            else:
+                pa = self._packed
+            self.ops.scatter(self._coords, self._lp, self._naccept, perm, split, pa, ns)
+            self.aux_launches += self.ops.launches_per_half_step
+
+    def _step_eager(self):
         it = self.iteration
         cur = it & 1
         self._perm = self._perm2[cur]
@@ -260,32 +319,86 @@ class EnsembleSampler:
                 self.ops.permutation(self._perm2[nxt], self.seed, it + 1)
                 self._perm_ready[nxt].record(self._side)
             self._perm_iter[nxt] = it + 1
-        for split in (0, 1):
-            ns = (W - split + 1) // 2
-            per, first, count = shard_bounds(ns, self.world, self.rank)
-            if count:
-                prop = self._prop[:count]
-                self.ops.propose(self._coords, self._perm, split, first, count, self.a, self.seed, it, prop,
-                                 self._factor)
-                self.engine.loglike_device(prop, out=self._lpnew[:count])
-                self.ops.accept(self._coords, self._lp, self._perm, split, first, count, prop, self._lpnew,
-                                self._factor, self.seed, it, self._packed)
-            if self.world > 1:
-                # static shape [per0, ndim+2] per rank; rows beyond `ns` are never read by scatter
-                self._all_gather(self._packed_all, self._packed)
-                if per != self.per0:       # odd ensembles: the second colour has one walker fewer -> re-pack rows
-                    pa = self._packed_all.view(self.world, self.per0, -1)[:, :per].reshape(-1, self.ndim + 2)
-                    pa = pa.contiguous()
-                else:
-                    pa = self._packed_all
-            else:
-                pa = self._packed
-            self.ops.scatter(self._coords, self._lp, self._naccept, self._perm, split, pa, ns)
-            self.aux_launches += self.ops.launches_per_half_step
+        self._half_steps(self._perm, it)
         if self._side is not None:
             self._step_done.record(torch.cuda.current_stream(self.device))
+
+    def _capture(self):
+        """Record one iteration as a CUDA graph.  Every kernel takes its Philox iteration as ``k + *iter_dev`` with the
+        counter in device memory, so the same graph is replayed for every iteration: the side branch sorts the
+        colouring permutation of iteration ``*iter_dev + 1`` while the main branch runs the two half-steps on the
+        current one; the tail copies it over and bumps the counter."""
+        ops, dev = self.ops, self.device
+        main = torch.cuda.current_stream(dev)
+        ops.iter_dev = self._iter_dev
+        try:
+            self._sync_graph_state()
+            ops.permutation(self._perm_next, self.seed, 1)      # creates the sort workspace outside the capture
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            launches0 = self.aux_launches
+            with torch.cuda.graph(g):
+                cap = torch.cuda.current_stream(dev)
+                self._side.wait_stream(cap)
+                with torch.cuda.stream(self._side):
+                    ops.permutation(self._perm_next, self.seed, 1)
+                self._half_steps(self._perm_g, 0)
+                cap.wait_stream(self._side)
+                self._perm_g.copy_(self._perm_next)
+                ops.advance(1)
+            self.aux_launches = launches0
+            self._graph = g
+        finally:
+            ops.iter_dev = None
+        del main
+
+    def _sync_graph_state(self):
+        """Device-side counter and current permutation = host-side ``self.iteration`` (first replay, or after the
+        counter was moved from outside)."""
+        ops = self.ops
+        self._iter_dev.fill_(self.iteration)
+        keep, ops.iter_dev = ops.iter_dev, self._iter_dev
+        try:
+            ops.permutation(self._perm_g, self.seed, 0)
+        finally:
+            ops.iter_dev = keep
+        self._iter_dev_value = self.iteration
+
+    def step(self):
+        """One stretch-move iteration: two half-steps, every walker proposed and evaluated once."""
+        if self.use_graph and self._graph_failed is None and self._steps_total >= self.GRAPH_EAGER_STEPS:
+            if self._graph is None:
+                try:
+                    self._capture()
+                except Exception as e:      # e.g. a collective backend that cannot be captured: stay eager, say so
+                    self._graph_failed = f"{type(e).__name__}: {e}"
+                    self._graph = None
+                    self.ops.iter_dev = None
+                    torch.cuda.synchronize(self.device)
+            if self._graph is not None:
+                if self._iter_dev_value != self.iteration:
+                    self._sync_graph_state()
+                self._graph.replay()
+                self._perm = self._perm_g
+                self.aux_launches += (2 * self.ops.launches_per_half_step + self.ops.launches_per_permutation + 2)
+                self.iteration += 1
+                self._iter_dev_value = self.iteration
+                self._steps_done += 1
+                self._steps_total += 1
+                return
+        self._step_eager()
         self.iteration += 1
         self._steps_done += 1
+        self._steps_total += 1
+
+    @property
+    def graph_active(self):
+        return self._graph is not None
+
+    def launches_per_step(self, kernels_per_loglike=6):
+        """Kernels of this library launched (or replayed) per ensemble iteration on this rank."""
+        n = 2 * (kernels_per_loglike + self.ops.launches_per_half_step) + getattr(self.ops, "launches_per_permutation", 0)
+        return n + (1 if self.graph_active else 0)              # + the counter kernel of the graph's tail
 
     # ------------------------------------------------------------------ emcee-like driver API
     def reset(self, nwalkers=None, ndim=None):

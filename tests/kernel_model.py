@@ -115,13 +115,13 @@ def _u01(hi, lo):
 def _draws(k, seed, iteration, split, purpose):
     seed, iteration = int(seed), int(iteration)
     return philox4x32_10(k.astype(np.uint32), np.uint32(iteration & 0xFFFFFFFF), np.uint32(iteration >> 32),
-                         np.uint32((split << 1) | purpose), np.uint32(seed & 0xFFFFFFFF), np.uint32(seed >> 32))
+                         np.uint32(purpose | (split << 2)), np.uint32(seed & 0xFFFFFFFF), np.uint32(seed >> 32))
 
 
 def split_permutation(nall, seed, iteration):
     """Model of jx_stretch_permutation: stable argsort of 64 Philox bits per walker.  The colour of the walker
     at position p is p & 1, i.e. emcee's ``inds = arange(n) % 2; random.shuffle(inds)``."""
-    r0, r1, _, _ = _draws(np.arange(nall), seed, iteration, 1, 0)      # (split << 1) | purpose == 2
+    r0, r1, _, _ = _draws(np.arange(nall), seed, iteration, 0, 2)      # purpose 2 = colouring keys (own Philox block)
     keys = (r0.astype(np.uint64) << np.uint64(32)) | r1.astype(np.uint64)
     return np.argsort(keys, kind="stable").astype(np.int32)
 
