@@ -11,14 +11,25 @@ evaluated once (two half-ensemble batches, emcee's red/blue split), i.e. 65,536 
 With N GPUs the 65,536 evaluations of a step are sharded over the ranks (strong scaling); the only
 collective is the all-gather of the accepted half-ensemble after each half-step.
 
-Prints ONE JSON line (rank 0).  `value` = evaluations / s with the ensemble resident in HBM;
-`e2e` = the same metric through the reference-facing call (`BatchedLikelihood.__call__`, the vectorised
-`getLikelihood`) with host numpy buffers in and out; `roofline` describes the dominant kernel (the map
-stage K3); `cpu_baseline` is the oracle's literal per-walker path on the host cores.
+Prints ONE JSON line (rank 0):
+
+* `value`      evaluations / s with the ensemble resident in HBM: the median of `timed_blocks` blocks of EXACTLY K
+               steps each (barrier + synchronize on both sides, CUDA events, max over ranks);
+* `e2e`        the same metric through the reference-facing call with HOST buffers (N = 1: the vectorised
+               `getLikelihood`, pinned host theta in, host log-likelihoods out; N > 1: the sampler iteration with the
+               ensemble state copied host -> device before and device -> host after every step, all-gathers inside);
+               `e2e_numpy` = `fit.getLikelihood(vals[W, ndim])` with a pageable numpy array, the call emcee makes;
+* `roofline`   the dominant kernel (the map stage) against the limit that binds it, the FP64 pipe: executed FP64
+               lane-operations / launch time / measured DFMA peak; the HBM form of SURVEY 8(d) is kept under `hbm_form`;
+* `cpu_baseline` the oracle's literal per-walker path on the host cores (bounded sample);
+* `secondary`  BASELINE configs 3 and 5 (synthetic 255- and 511-pixel clusters), 8,192 walkers per rank, outside the
+               headline timed region;
+* `state_checksum` 64-bit sums of the ensemble after the timed blocks: equal for every N (rank-count invariance).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -34,6 +45,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "log-likelihood evals/sec (walker-steps/s)"
 UNIT = "evals/s"
 TOTAL_WALKERS = 65536
+TIMED_BLOCKS = 5
 
 
 # ----------------------------------------------------------------------------------------------
@@ -50,35 +62,37 @@ WORKLOADS = {
 }
 
 
-def build_cluster():
+def build_cluster(workload=None):
     from joxsz_b200 import cluster
     from joxsz_b200.mb import mb
     mb.fit.debugfit = False
+    workload = workload or WORKLOAD
     inp = cluster.load_inputs_npz(os.path.join(ROOT, "tests", "golden", "cl1226_inputs.npz"))
-    if WORKLOADS[WORKLOAD] is not None:
-        map_half, nr = WORKLOADS[WORKLOAD]
+    if WORKLOADS[workload] is not None:
+        map_half, nr = WORKLOADS[workload]
         inp = cluster.synthetic_inputs(map_half=map_half, nr=nr, base=inp)
     fit, _ = cluster.build_fit(inp, savedir=None)
     return fit
 
 
-def workload_config(extra=None):
-    if WORKLOAD == "cl1226":
+def workload_config(walkers, n_gpus, workload=None):
+    """The `config` object: identical for the GPU arm and the reference arm of the same command line."""
+    workload = workload or WORKLOAD
+    if workload == "cl1226":
         cfg = {"workload": "CL J1226.9+3332 (shipped example) scaled to 65,536 walkers: Nr=313, map 171x171, "
                            "beam 55x55, 19 SZ points, 10 bands x 15 annuli, 13 free parameters; "
                            "step = one stretch-move ensemble iteration (65,536 likelihood evaluations)",
-               "walkers": TOTAL_WALKERS, "nr": 313, "map": 171, "ndim": 13}
+               "walkers": walkers, "nr": 313, "map": 171, "ndim": 13}
     else:
-        map_half, nr = WORKLOADS[WORKLOAD]
+        map_half, nr = WORKLOADS[workload]
         n = 2 * map_half + 1
         cfg = {"workload": f"synthetic cluster (joxsz_b200.cluster.synthetic_inputs): Nr={nr}, map {n}x{n} (the reference "
                            f"builds odd sides only), Gaussian beam 55x55, normal-cdf transfer function, shipped X-ray "
                            f"layout; step = one stretch-move ensemble iteration",
-               "walkers": TOTAL_WALKERS, "nr": nr, "map": n, "ndim": 13}
+               "walkers": walkers, "nr": nr, "map": n, "ndim": 13}
     cfg.update({"xray_tables": "synthetic (XSPEC unavailable)",
-                "l2_policy": "inputs and intermediates per step (> 400 MB) exceed the 126 MB L2; no flush needed"})
-    if extra:
-        cfg.update(extra)
+                "l2_policy": "inputs and intermediates per step (> 400 MB) exceed the 126 MB L2; no flush needed",
+                "parallelism": f"walkers sharded over {n_gpus} GPU(s)"})
     return cfg
 
 
@@ -152,7 +166,7 @@ def _cpu_init(workload="cl1226"):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     from helpers import oracle_setup_from_fit
-    _ORACLE_SETUP = oracle_setup_from_fit(build_cluster())
+    _ORACLE_SETUP = oracle_setup_from_fit(build_cluster(workload))
 
 
 def _cpu_eval(theta):
@@ -168,11 +182,11 @@ def cpu_reference_rate(thetas, pool):
     return len(thetas) / dt, dt, np.array(out)
 
 
-def make_pool():
+def make_pool(workload=None):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     ctx = mp.get_context("fork")
-    pool = ctx.Pool(cores, initializer=_cpu_init, initargs=(WORKLOAD,))
+    pool = ctx.Pool(cores, initializer=_cpu_init, initargs=(workload or WORKLOAD,))
     pool.map(_noop, range(cores * 2))
     return pool, cores
 
@@ -198,12 +212,14 @@ def run_reference_arm(args):
         t_tot += dt
     pool.close()
     rate = per_step * args.steps / t_tot
-    sample = f"{per_step} walkers per step of the 65,536-walker workload, literal per-walker path, Pool({cores})"
+    sample = f"{per_step} walkers per step of the {args.walkers}-walker workload, literal per-walker path, Pool({cores})"
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config({"reference_arm": "oracle port of joxsz_funcs.getLikelihood on host cores "
-                                                        "(the Python reference and its dependencies cannot travel)"}),
+            "config": workload_config(args.walkers, args.gpus),
+            "reference_arm": "oracle port of joxsz_funcs.getLikelihood on the host cores (the Python reference and its "
+                             "dependencies cannot travel to the GPU box); each step evaluates a bounded sample of the "
+                             "workload's walkers",
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -213,6 +229,136 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+
+def measured_fp64_peaks(device):
+    """FP64 FMA / DMMA peaks of this GPU from the microbenchmarks in scripts/libjx_peaks.so (measurement tooling,
+    not part of the product library)."""
+    from joxsz_b200 import build as jb
+    lib = C.CDLL(jb.build_peaks())
+    out = {}
+    for key, fn in (("dfma_tflops", "jxp_measure_fp64_tflops"), ("dmma_tflops", "jxp_measure_dmma_tflops")):
+        v = C.c_double(0.0)
+        f = getattr(lib, fn)
+        f.argtypes = [C.c_int32, C.POINTER(C.c_double)]
+        f.restype = C.c_int
+        out[key] = v.value if f(device, C.byref(v)) != 0 else v.value
+    return out
+
+
+def fp64_lane_ops(pk):
+    """Executed FP64 lane-operations (one DFMA / DADD / DMUL of one thread, counting the lanes a warp instruction
+    occupies) of the map kernel per walker, from the kernel's structure (cross-checked against
+    ncu's smsp__inst_executed_pipe_fp64 in profiles/)."""
+    H, P, nbeam = pk.H, pk.map_ops.P, int(pk.bmix.shape[0])
+    Q = P // 2 + 1
+    npair = (H + 1) // 2
+    fft9 = 9 * 2 * 230          # nine threads x (two DFT-16 + twiddles) ~ 230 FP64 instructions each per pass pair
+    if P == 256:
+        synth = (H * (H + 1) // 2) * 4
+        rows = 2 * npair * fft9 * 32 // 27               # 27 of 32 lanes carry a transform
+        ycols = 512 * 22 * (2 * nbeam - 1)               # 512 threads x 22 rows x (2 nbeam - 1) taps
+        return synth + rows + ycols
+    R = P // 256
+    synth = (H * (H + 1) // 2) * 4
+    rows = 2 * H * R * 16 * 2 * 230                      # sixteen-thread full-complex FFT-256 x R sub-transforms per row
+    ycols = ((H + 31) // 32 * 32) * Q * (2 * nbeam - 1)
+    return synth + rows + ycols
+
+
+def time_blocks(step_fn, steps, blocks, barrier, reduce_max):
+    import torch
+    out = []
+    for _ in range(blocks):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step_fn()
+        e1.record()
+        barrier()
+        out.append(reduce_max(e0.elapsed_time(e1)))
+    return out
+
+
+def state_checksum(sampler):
+    """64-bit wrapping sums of the bit patterns of the ensemble (positions, log-probs) and of the accept counters."""
+    import torch
+    c = sampler._coords.view(torch.int64).sum().item() & 0xFFFFFFFFFFFFFFFF
+    l = sampler._lp.view(torch.int64).sum().item() & 0xFFFFFFFFFFFFFFFF
+    a = int(sampler._naccept.sum().item())
+    return {"coords": f"{c:016x}", "log_prob": f"{l:016x}", "accepted": a, "iteration": sampler.iteration}
+
+
+def profile_pass(eng, sampler, steps):
+    """Per-kernel CUDA-event timers need kernel-by-kernel launches: `steps` more iterations of the same chain with the
+    graph suspended, right after the timed blocks.  Returns {stage: (total_ms, launches)}."""
+    import torch
+    eng.set_profiling(True)
+    eng.stage_times()
+    sampler.eager_only = True
+    for _ in range(steps):
+        sampler.step()
+    torch.cuda.synchronize()
+    st = eng.stage_times()
+    eng.set_profiling(False)
+    sampler.eager_only = False
+    return st
+
+
+def run_secondary(name, world, rank, local, dist, args, barrier, reduce_max):
+    """BASELINE configs 3 / 5: 8,192 walkers per rank of a larger synthetic cluster, a few iterations."""
+    import torch
+    from joxsz_b200.batched import BatchedLikelihood
+    from joxsz_b200.sampler import EnsembleSampler
+    t_build = time.perf_counter()
+    fit = build_cluster(name)
+    Wn = args.secondary_walkers * world
+    eng = BatchedLikelihood(fit, max_walkers=Wn // world // 2 + 64, device=local)
+    sampler = EnsembleSampler(Wn, eng.ndim, eng, seed=4321, world_size=world, rank=rank,
+                              group=(dist.group.WORLD if world > 1 else None))
+    sampler.initialize(ensemble(fit, Wn, seed=20260105))
+    t_build = time.perf_counter() - t_build
+    steps = args.secondary_steps
+    for _ in range(3):
+        sampler.step()
+    blocks = time_blocks(sampler.step, steps, 3, barrier, reduce_max)
+    ms = sorted(blocks)[len(blocks) // 2]
+    chk = state_checksum(sampler)
+    stages = profile_pass(eng, sampler, 2)
+    out = None
+    if rank == 0:
+        pk = eng.packed
+        ncalls = max(stages["szmap"][1], 1)
+        stage_ms = {k: v[0] / ncalls for k, v in stages.items()}
+        nw = sampler.evals_per_rank_per_launch()
+        lane = fp64_lane_ops(pk)
+        k3_s = stage_ms["szmap"] * 1e-3
+        # parity of the device path against the literal per-walker oracle on a small sample of the final ensemble
+        theta = sampler.coords_host()[:args.secondary_cpu_sample]
+        pool, cores = make_pool(name)
+        cpu_rate, cpu_dt, cpu_ll = cpu_reference_rate(theta, pool)
+        pool.close()
+        gpu_ll = eng(theta)
+        fin = np.isfinite(cpu_ll)
+        out = {"config": workload_config(Wn, world, name), "value": Wn * steps / (ms * 1e-3), "unit": UNIT,
+               "ms_per_step": ms / steps, "steps": steps, "timed_blocks": len(blocks),
+               "block_ms": [b / steps for b in blocks], "graph": sampler.graph_active,
+               "map_kernel": "k3l_szmap_kernel" if pk.map_ops.P != 256 else "k3_szmap_kernel",
+               "stage_ms_per_launch": stage_ms, "walkers_per_launch": nw,
+               "map_kernel_fp64_lane_ops_per_walker": lane,
+               "map_kernel_fp64_lane_ops_per_s": lane * nw / k3_s if k3_s > 0 else None,
+               "map_kernel_hbm_form_gbs": pk.algorithmic_bytes()["szmap"] * nw / k3_s / 1e9 if k3_s > 0 else None,
+               "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{len(theta)} walkers, literal per-walker oracle path, {cpu_dt:.1f} s"},
+               "parity_max_abs_dll_vs_cpu_sample": float(np.max(np.abs(gpu_ll[fin] - cpu_ll[fin]))) if fin.any() else None,
+               "parity_inf_mask_equal": bool(np.array_equal(fin, np.isfinite(gpu_ll))),
+               "state_checksum": chk, "setup_s": t_build,
+               "peak_memory_gb": torch.cuda.max_memory_allocated() / 1e9}
+    eng.close()
+    del sampler, eng
+    torch.cuda.empty_cache()
+    return out
+
 
 def run_gpu_arm(args):
     import torch
@@ -227,15 +373,16 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    from joxsz_b200 import funcs
     from joxsz_b200.batched import BatchedLikelihood
     from joxsz_b200.sampler import EnsembleSampler
 
     fit = build_cluster()
     W = args.walkers
-    eng = BatchedLikelihood(fit, max_walkers=max(W // world + 64, 1024), device=local)
+    eng = BatchedLikelihood(fit, max_walkers=max(W // world + 64, 1024) if world > 1 else W, device=local)
     p0 = ensemble(fit, W)
     sampler = EnsembleSampler(W, eng.ndim, eng, seed=1234, world_size=world, rank=rank,
-                              group=(dist.group.WORLD if world > 1 else None))
+                              group=(dist.group.WORLD if world > 1 else None), graph=not args.no_graph)
     sampler.initialize(p0)
 
     def barrier():
@@ -243,57 +390,96 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(args.warmup):
         sampler.step()
-    eng.set_profiling(True)
-    eng.stage_times()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    extra_warm = 0
+    while sampler.use_graph and not sampler.graph_active and sampler._graph_failed is None and extra_warm < 4:
+        sampler.step()                       # the iteration is captured after its first eager steps
+        extra_warm += 1
     with ClockSampler(local) as clk:
-        ev0.record()
-        for _ in range(args.steps):
-            sampler.step()
-        ev1.record()
-        barrier()
-    ms = ev0.elapsed_time(ev1)
-    stages = eng.stage_times()
-    eng.set_profiling(False)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+        blocks = time_blocks(sampler.step, args.steps, TIMED_BLOCKS, barrier, reduce_max)
+    ms = sorted(blocks)[len(blocks) // 2]
     value = W * args.steps / (ms * 1e-3)
     acc = sampler.mean_acceptance()
+    checksum = state_checksum(sampler)
+    stages = profile_pass(eng, sampler, args.steps)
 
-    # ---- end to end through the reference-facing vectorised call with host buffers (rank-local shard)
+    # ---- end to end with host buffers
     shard = W // world
-    host_theta = sampler.coords_host()[rank * shard:(rank + 1) * shard].copy()
-    # the step's inputs live in pinned host memory (the caller's buffer); every call copies them to the device,
-    # runs the kernels and reads the log-likelihoods back
-    host_theta_pinned = torch.from_numpy(host_theta).pin_memory()
-    for _ in range(2):
-        eng(host_theta_pinned)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        out = eng(host_theta_pinned).numpy()     # pinned host tensor in (H2D), kernels, D2H, host array out -- every step
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_wall_s = time.perf_counter() - t0
-    e2e_s = max(e0.elapsed_time(e1) * 1e-3, e2e_wall_s)      # device clock; the host clock can only be longer
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = shard * world * args.steps / float(t.item())
-    assert np.isfinite(out).any()
+    host_state = sampler.coords_host()
+    if world == 1:
+        host_theta = host_state.copy()
+        # the step's inputs live in pinned host memory (the caller's buffer); every call copies them to the device,
+        # runs the kernels and reads the log-likelihoods back
+        host_theta_pinned = torch.from_numpy(host_theta).pin_memory()
+        out_holder = {}
 
+        def e2e_step():
+            out_holder["ll"] = eng(host_theta_pinned).numpy()
+
+        for _ in range(2):
+            e2e_step()
+        t0 = time.perf_counter()
+        e2e_blocks = time_blocks(e2e_step, args.steps, 3, barrier, reduce_max)
+        e2e_ms = sorted(e2e_blocks)[1]
+        assert np.isfinite(out_holder["ll"]).any()
+        e2e = {"value": W * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(W * eng.ndim * 8),
+               "d2h_bytes_per_step": int(W * 8), "block_ms": [b / args.steps for b in e2e_blocks],
+               "call": "BatchedLikelihood.__call__(pinned host theta[65536, 13]) -> host ll (the vectorised getLikelihood)"}
+        # the call emcee makes (joxsz_main.py:206): the bound fit.getLikelihood on a pageable numpy array
+        funcs.attach_engine(fit, eng)
+        vals = host_theta.copy()
+
+        def e2e_numpy_step():
+            out_holder["ll2"] = fit.getLikelihood(vals)
+
+        for _ in range(2):
+            e2e_numpy_step()
+        nb = time_blocks(e2e_numpy_step, args.steps, 3, barrier, reduce_max)
+        assert np.array_equal(out_holder["ll2"], out_holder["ll"])
+        funcs.detach_engine(fit)
+        e2e_numpy = {"value": W * args.steps / (sorted(nb)[1] * 1e-3), "unit": UNIT,
+                     "call": "fit.getLikelihood(vals[65536, 13]) with a pageable numpy array (staged through the engine's "
+                             "pinned buffer), host array out"}
+    else:
+        # N > 1: the sampler iteration with the ensemble state in host memory between steps -- H2D of positions and
+        # log-probs before, the two half-steps with their all-gathers, D2H of the new state after
+        pin_c = torch.from_numpy(host_state.copy()).pin_memory()
+        pin_l = torch.from_numpy(sampler.log_prob_host().copy()).pin_memory()
+
+        def e2e_step():
+            sampler._coords.copy_(pin_c, non_blocking=True)
+            sampler._lp.copy_(pin_l, non_blocking=True)
+            sampler.step()
+            pin_c.copy_(sampler._coords, non_blocking=True)
+            pin_l.copy_(sampler._lp, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        e2e_blocks = time_blocks(e2e_step, args.steps, 3, barrier, reduce_max)
+        e2e_ms = sorted(e2e_blocks)[1]
+        nbytes = int(W * (eng.ndim + 1) * 8)
+        e2e = {"value": W * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes, "block_ms": [b / args.steps for b in e2e_blocks],
+               "call": "EnsembleSampler.step() with the ensemble state (positions, log-probs) copied from pinned host "
+                       "memory before and back after every iteration, on every rank; all-gathers inside"}
+        e2e_numpy = None
+        host_theta = host_state[rank * shard:(rank + 1) * shard].copy()
+
+    line = None
     if rank == 0:
         pk = eng.packed
         alg = pk.algorithmic_bytes()
+        flops = pk.algorithmic_flops()
         k3_ms, k3_n = stages["szmap"]
-        k3_walkers = sampler.evals_per_rank_per_launch()
+        nw = sampler.evals_per_rank_per_launch()
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -301,70 +487,63 @@ def run_gpu_arm(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        k3_avg_s = (k3_ms / max(k3_n, 1)) * 1e-3
-        achieved = alg["szmap"] * k3_walkers / k3_avg_s / 1e9 if k3_n else None
-        import ctypes as C
-        tf = C.c_double(0.0)
-        eng.lib.jx_measure_fp64_tflops(local, C.byref(tf))
-        tfd = C.c_double(0.0)
-        eng.lib.jx_measure_dmma_tflops(local, C.byref(tfd))
-        flops = pk.algorithmic_flops()
-        roof = {"bound": "hbm", "kernel": "k3_szmap_kernel" if WORKLOAD == "cl1226" else "k3l_szmap_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                "alg_bytes_per_walker": alg["szmap"], "walkers_per_launch": k3_walkers,
-                "avg_launch_ms": k3_avg_s * 1e3, "launches_timed": int(k3_n),
-                "note": "algorithmic bytes = the maps of the stages this kernel replaces, materialised once (write y_2d, "
-                        "read y_2d, write the convolved map; SURVEY 8d convention); the kernel keeps them in shared "
-                        "memory and writes only the distinct pixels of the convolved map, so DRAM traffic is far below "
-                        "this and the binding limit is FP64 throughput.  The filter stage is the K7 GEMM "
-                        "(stage_rooflines.filter); stage_rooflines.szmap_plus_filter has both against the same bytes",
-                "fp64": {"alg_flops_per_walker": flops["szmap"], "measured_dfma_peak_tflops": tf.value, "measured_dmma_peak_tflops": tfd.value,
-                         "achieved_tflops": flops["szmap"] * k3_walkers / k3_avg_s / 1e12 if k3_n else None}}
-        ncalls = max(k3_n, 1)
-        stage_ms = {k: (v[0] / ncalls) for k, v in stages.items()}
-        # DRAM traffic of the dominant kernel from the committed ncu capture of this same command (per launch)
+        fp = measured_fp64_peaks(local)
+        k3_s = (k3_ms / max(k3_n, 1)) * 1e-3
+        lane = fp64_lane_ops(pk)
+        lane_rate = lane * nw / k3_s if k3_n else None
+        lane_peak = fp["dfma_tflops"] * 1e12 / 2.0            # one DFMA = 2 flop = one lane-operation
+        hbm_gbs = alg["szmap"] * nw / k3_s / 1e9 if k3_n else None
+        map_kernel = "k3_szmap_kernel" if pk.map_ops.P == 256 else "k3l_szmap_kernel"
+        roof = {"bound": "fp64", "kernel": map_kernel,
+                "achieved": 2.0 * lane_rate / 1e12 if lane_rate else None, "peak": fp["dfma_tflops"], "unit": "TFLOP/s",
+                "frac": lane_rate / lane_peak if lane_rate and lane_peak else None, "traffic": None,
+                "peak_source": "DFMA microbenchmark in this run (scripts/jx_peaks.cu); MEASURED_PEAKS.json has no FP64 figure",
+                "executed_fp64_lane_ops_per_walker": lane, "walkers_per_launch": nw,
+                "avg_launch_ms": k3_s * 1e3, "launches_timed": int(k3_n),
+                "timing": "CUDA events around every kernel in an eager pass of `steps` iterations right after the timed "
+                          "blocks (the timed blocks replay one CUDA graph per iteration, which has no per-kernel events)",
+                "note": "achieved = executed FP64 lane-operations x 2 flop / launch time; the kernel keeps the maps in "
+                        "shared memory, so its DRAM traffic is a few per cent of the staged-reference bytes and HBM is "
+                        "not what binds it (hbm_form, kept for SURVEY 8d's convention)",
+                "hbm_form": {"alg_bytes_per_walker": alg["szmap"], "achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak,
+                             "frac": hbm_gbs / hbm_peak if hbm_gbs else None, "peak_source": peak_src},
+                "alg_flops_per_walker_survey_8d": flops["szmap"]}
         try:
             if WORKLOAD != "cl1226":
                 raise KeyError("no ncu capture for this workload")
             tr = json.load(open(os.path.join(ROOT, "profiles", "k3_ncu_traffic.json")))
-            roof["traffic"] = tr["dram_bytes_per_launch"] * (k3_walkers / tr["walkers_per_launch"])
+            roof["traffic"] = tr["dram_bytes_per_launch"] * (nw / tr["walkers_per_launch"])
             roof["traffic_source"] = tr.get("source")
-            # what the kernel is actually bound by, from the same ncu capture (pipe-busy fractions of the SMs)
-            roof["executed"] = {k: tr[k] for k in ("fp64_pipe_busy_frac", "shared_pipe_busy_frac",
-                                                   "issue_slots_busy_frac") if k in tr}
+            roof["ncu"] = {k: tr[k] for k in ("fp64_pipe_busy_frac", "shared_pipe_busy_frac", "issue_slots_busy_frac",
+                                              "fp64_lane_ops_per_walker") if k in tr}
         except Exception:
             pass
-        # every stage against the roofline north_star names for it: HBM for profiles / map / reduction,
-        # FP64 tensor (DMMA) peak for the projection GEMM.  Algorithmic figures: SURVEY.md 8(d), DESIGN.md 5.
-        nw = k3_walkers
+        ncalls = max(k3_n, 1)
+        stage_ms = {k: (v[0] / ncalls) for k, v in stages.items()}
+
         def hbm(stage, key):
             t_s = stage_ms[stage] * 1e-3
             gbs = alg[key] * nw / t_s / 1e9 if t_s > 0 else None
             return {"bound": "hbm", "alg_bytes_per_walker": alg[key], "ms": stage_ms[stage], "achieved_gbs": gbs,
                     "frac_of_measured_hbm": gbs / hbm_peak if gbs else None}
-        proj_tf = flops["project"] * nw / (stage_ms["project"] * 1e-3) / 1e12 if stage_ms["project"] > 0 else None
-        filt_tf = flops["filter"] * nw / (stage_ms["filter"] * 1e-3) / 1e12 if stage_ms.get("filter", 0) > 0 else None
+
+        def tensor(stage, key):
+            t_s = stage_ms.get(stage, 0.0) * 1e-3
+            tf = flops[key] * nw / t_s / 1e12 if t_s > 0 else None
+            return {"bound": "tensor(fp64 dmma)", "alg_flops_per_walker": flops[key], "ms": stage_ms.get(stage),
+                    "achieved_tflops": tf, "peak_tflops_measured_dmma": fp["dmma_tflops"],
+                    "frac": tf / fp["dmma_tflops"] if tf and fp["dmma_tflops"] else None}
+
         both_s = (stage_ms["szmap"] + stage_ms.get("filter", 0.0)) * 1e-3
         both_gbs = alg["szmap"] * nw / both_s / 1e9 if both_s > 0 else None
-        stage_roof = {"profiles": hbm("profiles", "profiles"), "szmap": hbm("szmap", "szmap"),
-                      "xray": dict(hbm("xray", "xray"), note="side stream: elapsed time overlaps the project / szmap stages "
-                                   "(0.105 ms per 32768 walkers when run alone)"),
-                      "tail": hbm("tail", "tail"),
-                      # the transfer-function filter is a GEMM over the walkers (K7) when the cyclic length is 256
-                      "filter": {"bound": "tensor(fp64 dmma)", "alg_flops_per_walker": flops["filter"],
-                                 "ms": stage_ms.get("filter"), "achieved_tflops": filt_tf,
-                                 "peak_tflops_measured_dmma": tfd.value,
-                                 "frac": filt_tf / tfd.value if filt_tf and tfd.value else None},
-                      # north_star item (3) as a whole: map synthesis + beam convolution + filtering
+        stage_roof = {"profiles": hbm("profiles", "profiles"),
+                      "szmap": {"bound": "fp64", "ms": stage_ms["szmap"], "frac": roof["frac"]},
+                      "xray": dict(hbm("xray", "xray"), note="side stream: elapsed time overlaps the project / szmap stages"),
+                      "tail": hbm("tail", "tail"), "filter": tensor("filter", "filter"), "project": tensor("project", "project"),
                       "szmap_plus_filter": {"bound": "hbm", "alg_bytes_per_walker": alg["szmap"], "ms": both_s * 1e3,
                                             "achieved_gbs": both_gbs,
-                                            "frac_of_measured_hbm": both_gbs / hbm_peak if both_gbs else None},
-                      "project": {"bound": "tensor(fp64 dmma)", "alg_flops_per_walker": flops["project"],
-                                  "ms": stage_ms["project"], "achieved_tflops": proj_tf,
-                                  "peak_tflops_measured_dmma": tfd.value,
-                                  "frac": proj_tf / tfd.value if proj_tf and tfd.value else None}}
-        launches = int(sum(v[1] for v in stages.values())) + sampler.aux_launches
-        # bounded CPU baseline on this box's cores
+                                            "frac_of_measured_hbm": both_gbs / hbm_peak if both_gbs else None}}
+        # bounded CPU baseline on this box's cores + parity of the device path on the same walkers
         pool, cores = make_pool()
         sample_n = max(cores * 64, 512)
         cpu_rate, cpu_dt, cpu_ll = cpu_reference_rate(host_theta[:sample_n], pool)
@@ -375,20 +554,36 @@ def run_gpu_arm(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config({"walkers": W, "parallelism": f"walkers sharded over {world} GPU(s)",
-                                           "acceptance_fraction": acc}),
-                "clocks": clk.summary(),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(shard * eng.ndim * 8),
-                        "d2h_bytes_per_step": int(shard * 8),
-                        "call": "BatchedLikelihood.__call__(pinned host theta) -> host ll (vectorised getLikelihood)"},
-                "gpu_launches": launches,
-                "roofline": roof,
-                "stage_ms_per_launch": stage_ms,
-                "stage_rooflines": stage_roof,
+                "config": workload_config(W, world),
+                "timed_blocks": TIMED_BLOCKS, "block_ms_per_step": [b / args.steps for b in blocks],
+                "value_is": "median block", "warmup_extra_steps": extra_warm,
+                "acceptance_fraction": acc, "state_checksum": checksum,
+                "sampler": {"cuda_graph": sampler.graph_active, "graph_fallback_reason": sampler._graph_failed},
+                "clocks": clk.summary(), "e2e": e2e, "e2e_numpy": e2e_numpy,
+                "gpu_launches": int(sampler.launches_per_step() * args.steps),
+                "gpu_launches_note": "kernels of libjoxsz_b200.so per timed block (K steps), replayed from one CUDA graph "
+                                     "per iteration: 2 x (K1 K4 K2 K3 K7 K5 + propose accept scatter) + permutation",
+                "roofline": roof, "stage_ms_per_launch": stage_ms, "stage_rooflines": stage_roof,
                 "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
                                  "sample": f"{sample_n} walkers of the same ensemble, literal per-walker oracle path, "
                                            f"Pool({cores}), {cpu_dt:.1f} s"},
                 "parity_max_abs_dll_vs_cpu_sample": parity}
+    eng.close()
+    del sampler, eng
+    torch.cuda.empty_cache()
+
+    if args.secondary and WORKLOAD == "cl1226":
+        sec = {}
+        for name in ("synth255", "synth511"):
+            try:
+                r = run_secondary(name, world, rank, local, dist, args, barrier, reduce_max)
+            except Exception as e:          # the headline line must still be printed
+                r = {"error": f"{type(e).__name__}: {e}"}
+            if rank == 0:
+                sec[name] = r
+        if rank == 0:
+            line["secondary"] = sec
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -404,6 +599,12 @@ def main():
     ap.add_argument("--workload", default="cl1226", choices=sorted(WORKLOADS),
                     help="cl1226 = the configuration the metric is quoted on (default); synth255 / synth511 = the "
                          "larger synthetic clusters of BASELINE configs 3 and 5")
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false",
+                    help="skip the BASELINE config 3 / 5 block")
+    ap.add_argument("--secondary-walkers", type=int, default=8192, help="walkers per rank in the secondary block")
+    ap.add_argument("--secondary-steps", type=int, default=3)
+    ap.add_argument("--secondary-cpu-sample", type=int, default=32)
+    ap.add_argument("--no-graph", action="store_true", help="launch the sampler iteration kernel by kernel")
     args = ap.parse_args()
     global WORKLOAD
     WORKLOAD = args.workload

@@ -80,6 +80,22 @@ def jx_invalidate(fit):
     _drop_engine(id(fit))
 
 
+def attach_engine(fit, eng):
+    """Make ``eng`` (a :class:`BatchedLikelihood` built for ``fit``) the engine ``fit.getLikelihood`` uses, instead of
+    letting the first call build one (a caller that already sized an engine for its ensemble)."""
+    import weakref
+    key = id(fit)
+    ent = _ENGINES.get(key)
+    if ent is not None and ent[1] is not eng:
+        _drop_engine(key)
+    _ENGINES[key] = (weakref.ref(fit, lambda _r, k=key: _drop_engine(k)), eng, _signature(fit))
+
+
+def detach_engine(fit):
+    """Forget the engine of ``fit`` without closing it (the caller owns it)."""
+    _ENGINES.pop(id(fit), None)
+
+
 def engine_for(fit, min_walkers=1):
     """The fit's :class:`BatchedLikelihood`, (re)built on demand."""
     import weakref

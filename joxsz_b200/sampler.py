@@ -180,6 +180,7 @@ class EnsembleSampler:
             raise ValueError("graph=True needs the CUDA stretch-move kernels")
         self._graph = None
         self._graph_failed = None
+        self.eager_only = False               # True: launch kernel by kernel even if a graph exists (per-kernel timers)
         self.initspread = 0.1
         self.pos0 = None
         self.backend = self                   # mcmc.backend.get_chain()/get_log_prob()/reset(...)
@@ -366,7 +367,8 @@ class EnsembleSampler:
 
     def step(self):
         """One stretch-move iteration: two half-steps, every walker proposed and evaluated once."""
-        if self.use_graph and self._graph_failed is None and self._steps_total >= self.GRAPH_EAGER_STEPS:
+        if (self.use_graph and not self.eager_only and self._graph_failed is None
+                and self._steps_total >= self.GRAPH_EAGER_STEPS):
             if self._graph is None:
                 try:
                     self._capture()

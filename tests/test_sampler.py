@@ -259,3 +259,122 @@ def test_mcmc_run_schedule_end_to_end(cl1226_fit, cl1226_oracle, tmp_path):
         assert [k.decode() for k in z["param_names"]] == list(fit.thawed) and int(z["burn"]) == nburn
     finally:
         fit.updateThawed(saved)
+
+
+def test_shuffle_and_proposal_streams_are_independent():
+    """the colouring keys and the split-1 proposal draws once shared a Philox block, which made a walker's
+    stretch factor a function of its rank in the permutation.  Every (purpose, split) pair has its own counter word."""
+    k = np.arange(4096)
+    seed, it = 99, 1234
+    blocks = {}
+    for purpose in (0, 1, 2):
+        for split in (0, 1):
+            if purpose == 2 and split == 1:
+                continue
+            r = km._draws(k, seed, it, split, purpose)
+            blocks[(purpose, split)] = (r[0].astype(np.uint64) << np.uint64(32)) | r[1].astype(np.uint64)
+    keys = list(blocks)
+    for i in range(len(keys)):
+        for j in range(i + 1, len(keys)):
+            assert not np.any(blocks[keys[i]] == blocks[keys[j]]), (keys[i], keys[j])
+    # z of the split-1 walkers does not depend on their position in the colouring permutation
+    nall = 4096
+    perm = split_permutation(nall, seed, it)
+    pos = np.empty(nall, dtype=np.int64)
+    pos[perm] = np.arange(nall)
+    active = perm[1::2]
+    u = blocks[(0, 1)][active].astype(np.float64) / 2.0 ** 64
+    rho = np.corrcoef(u, pos[active])[0, 1]
+    assert abs(rho) < 4.0 / np.sqrt(active.size)
+    first = perm[1]                               # the smallest key of colour 1: its draw is an ordinary uniform
+    assert blocks[(0, 1)][first] != blocks[(2, 0)][first]
+
+
+@pytest.mark.gpu
+def test_graph_replay_equals_eager_steps(cl1226_fit):
+    """One iteration captured as a CUDA graph (device-side Philox counter) gives the chain of the launch-by-launch
+    path bit for bit, including after the counter is moved and after a new ensemble is loaded."""
+    from joxsz_b200.batched import BatchedLikelihood
+    from joxsz_b200.synthetic import draw_parameters
+    eng = BatchedLikelihood(cl1226_fit, max_walkers=256)
+    for W in (64, 51):
+        p0 = draw_parameters(cl1226_fit.thawed, n=W, seed=8, spread=0.01)
+        a = EnsembleSampler(W, eng.ndim, eng, seed=5, graph=True)
+        b = EnsembleSampler(W, eng.ndim, eng, seed=5, graph=False)
+        for s in (a, b):
+            s.initialize(p0)
+            for _ in range(7):
+                s.step()
+        assert a.graph_active and not b.graph_active and a._graph_failed is None
+        assert np.array_equal(a.coords_host(), b.coords_host())
+        assert np.array_equal(a.log_prob_host(), b.log_prob_host())
+        assert np.array_equal(a.acceptance_fraction, b.acceptance_fraction)
+        for s in (a, b):
+            s.iteration += 1000                   # a jump of the counter (e.g. a restart that skips draws)
+            s.initialize(p0 * (1 + 1e-4))
+            for _ in range(3):
+                s.step()
+        assert np.array_equal(a.coords_host(), b.coords_host())
+        assert np.array_equal(a.log_prob_host(), b.log_prob_host())
+    eng.close()
+
+
+def _nccl_worker(rank, world, port, W, steps, graph, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from joxsz_b200 import cluster
+    from joxsz_b200.batched import BatchedLikelihood
+    from joxsz_b200.mb import mb
+    from joxsz_b200.synthetic import draw_parameters
+    mb.fit.debugfit = False
+    inp = cluster.load_inputs_npz(os.path.join(ROOT, "tests", "golden", "cl1226_inputs.npz"))
+    fit, _ = cluster.build_fit(inp, savedir=None)
+    eng = BatchedLikelihood(fit, max_walkers=256, device=rank)
+    p0 = draw_parameters(fit.thawed, n=W, seed=8, spread=0.01)
+    s = EnsembleSampler(W, eng.ndim, eng, seed=5, world_size=world, rank=rank, group=dist.group.WORLD, graph=graph)
+    s.initialize(p0)
+    for _ in range(steps):
+        s.step()
+    q.put((rank, s.coords_host(), s.log_prob_host(), s.acceptance_fraction, s.graph_active, s._graph_failed))
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", [False, True])
+def test_two_nccl_ranks_reproduce_single_gpu_chain(cl1226_fit, graph):
+    """Hardware proof of rank-count invariance: 2 processes / 2 GPUs over NCCL end with the ensemble of the 1-GPU run,
+    bit for bit (eager launches and the captured graph with the all-gathers inside)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    from joxsz_b200.batched import BatchedLikelihood
+    from joxsz_b200.synthetic import draw_parameters
+    W, steps, world = 70, 6, 2
+    eng = BatchedLikelihood(cl1226_fit, max_walkers=256)
+    ref = EnsembleSampler(W, eng.ndim, eng, seed=5, graph=False)
+    ref.initialize(draw_parameters(cl1226_fit.thawed, n=W, seed=8, spread=0.01))
+    for _ in range(steps):
+        ref.step()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, W, steps, graph, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, coords, lp, acc, active, failed in res:
+        assert active == graph, failed
+        assert np.array_equal(coords, ref.coords_host())
+        assert np.array_equal(lp, ref.log_prob_host())
+        assert np.array_equal(acc, ref.acceptance_fraction)
+    eng.close()
