@@ -313,7 +313,7 @@ def run_secondary(name, world, rank, local, dist, args, barrier, reduce_max):
     t_build = time.perf_counter()
     fit = build_cluster(name)
     Wn = args.secondary_walkers * world
-    eng = BatchedLikelihood(fit, max_walkers=Wn // world // 2 + 64, device=local)
+    eng = BatchedLikelihood(fit, max_walkers=Wn // world + 64, device=local)
     sampler = EnsembleSampler(Wn, eng.ndim, eng, seed=4321, world_size=world, rank=rank,
                               group=(dist.group.WORLD if world > 1 else None))
     sampler.initialize(ensemble(fit, Wn, seed=20260105))
