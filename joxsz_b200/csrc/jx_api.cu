@@ -399,7 +399,9 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
             rc = fail(h, JX_ERR_INVALID, "map kernel needs more shared memory than the device offers");
         } else {
             d.k3_direct = jx_szmap_direct_ok(d) ? 1 : 0;
+            d.k3_ws = d.k3_direct && jx_szmap_ws_ok(d) && jx_szmap_ws_smem_bytes(d) <= (size_t)prop.sharedMemPerBlockOptin ? 1 : 0;
             cudaError_t e = jx_szmap_configure(d);
+            if (e == cudaSuccess && d.k3_ws) e = jx_szmap_ws_configure(d);
             if (e == cudaSuccess) e = jx_filter_configure(d);
             if (e != cudaSuccess) rc = cuda_fail(h, e, "configure map / filter kernels");
         }
@@ -438,7 +440,8 @@ static cudaError_t launch_map_filter(jx_handle* h, const double* coef, const uin
     const jx_dev& d = h->d;
     cudaError_t e;
     if (d.npad == 256) {
-        e = jx_launch_szmap(d, coef, flags, W, h->sm_count, convq, d.ws_tri, st);
+        e = d.k3_ws ? jx_launch_szmap_ws(d, coef, flags, W, h->sm_count, convq, d.ws_tri, st)
+                    : jx_launch_szmap(d, coef, flags, W, h->sm_count, convq, d.ws_tri, st);
         if (e == cudaSuccess && ev_mid) e = cudaEventRecord(ev_mid, st);
         if (e != cudaSuccess) return e;
         *row = d.ws_rowp; *ld_row = d.hpf; *nparts = jx_filter_parts(d);

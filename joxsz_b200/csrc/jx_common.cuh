@@ -49,6 +49,7 @@ struct jx_dev {
     const double* bhat;      // [nq, nq]
     int nbeam;               // beam half-side incl. the centre
     int k3_direct;           // map kernel convolves along y directly (jx_szmap_direct_ok at jx_create)
+    int k3_ws;               // two walkers in flight per SM: the warp-specialised map kernel (k3w_szmap.cu)
     const double* bmix;      // [28, bmix_pitch] beam in (y offset, kx), zero rows beyond nbeam; NULL when nbeam > 28
     int bmix_pitch;          // JX_BMIX_PITCH for the cyclic length 256, nq rounded up to 4 otherwise
     const double* cmat_t;    // [nh, nh] transposed on upload: [kx, v]
@@ -158,6 +159,12 @@ cudaError_t jx_launch_tap_expand(const jx_dev& d, const double* convq, int W, do
 cudaError_t jx_launch_tap_mapout(const jx_dev& d, const double* convq, int W, double* mapout, double* scratch,
                                  cudaStream_t st);
 size_t jx_szmap_smem_bytes(const jx_dev& d);
+// warp-specialised form of the map stage, two walkers in flight per SM (k3w_szmap.cu)
+bool jx_szmap_ws_ok(const jx_dev& d);
+size_t jx_szmap_ws_smem_bytes(const jx_dev& d);
+cudaError_t jx_szmap_ws_configure(const jx_dev& d);
+cudaError_t jx_launch_szmap_ws(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
+                               double* convq, double* tri, cudaStream_t st);
 // large-map path (cyclic length 512 / 1024, working set in an L2-resident global scratch): k3l_szmap.cu
 bool jx_szmap_large_supported(const jx_dev& d);
 size_t jx_szmap_large_smem_bytes(const jx_dev& d);

@@ -141,7 +141,7 @@ class EnsembleSampler:
     """
 
     def __init__(self, nwalkers, ndim, log_prob_fn, pool=None, backend=None, a=2.0, seed=None, world_size=1,
-                 rank=0, group=None, ops=None, device=None, vectorize=True, moves=None, graph=None):
+                 rank=0, group=None, ops=None, device=None, vectorize=True, moves=None, graph=None, chain_shard=False):
         if nwalkers < 2 * ndim:
             raise ValueError("The number of walkers needs to be at least twice the dimension of the problem")
         if moves is not None:
@@ -178,6 +178,13 @@ class EnsembleSampler:
         self.use_graph = isinstance(self.ops, CudaStretchOps) if graph is None else bool(graph)
         if self.use_graph and not isinstance(self.ops, CudaStretchOps):
             raise ValueError("graph=True needs the CUDA stretch-move kernels")
+        #: True: a rank keeps only the chain of its own walkers [rank*W/world, (rank+1)*W/world) -- every rank holds the
+        #: whole ensemble state, but the stored chain of a long many-walker run (nsteps x W x ndim doubles) need not be
+        #: replicated on every GPU; get_chain() / get_log_prob() then return the local shard
+        self.chain_shard = bool(chain_shard) and self.world > 1
+        lo = (self.nwalkers * self.rank) // self.world if self.chain_shard else 0
+        hi = (self.nwalkers * (self.rank + 1)) // self.world if self.chain_shard else self.nwalkers
+        self.chain_walkers = (lo, hi)
         self._graph = None
         self._graph_failed = None
         self.eager_only = False               # True: launch kernel by kernel even if a graph exists (per-kernel timers)
@@ -448,8 +455,9 @@ class EnsembleSampler:
         for i in range(1, total + 1):
             self.step()
             if store and i % checkpoint_step == 0:
-                self._chain[self._nstored].copy_(self._coords)
-                self._chain_lp[self._nstored].copy_(self._lp)
+                lo, hi = self.chain_walkers
+                self._chain[self._nstored].copy_(self._coords[lo:hi])
+                self._chain_lp[self._nstored].copy_(self._lp[lo:hi])
                 self._nstored += 1
             if bar is not None:
                 bar.update(1)
@@ -466,12 +474,13 @@ class EnsembleSampler:
 
     def _grow(self, nsave):
         need = self._nstored + nsave
+        nw = self.chain_walkers[1] - self.chain_walkers[0]
         if self._chain is None:
-            self._chain = torch.empty((need, self.nwalkers, self.ndim), dtype=torch.float64, device=self.device)
-            self._chain_lp = torch.empty((need, self.nwalkers), dtype=torch.float64, device=self.device)
+            self._chain = torch.empty((need, nw, self.ndim), dtype=torch.float64, device=self.device)
+            self._chain_lp = torch.empty((need, nw), dtype=torch.float64, device=self.device)
         elif self._chain.shape[0] < need:
-            c = torch.empty((need, self.nwalkers, self.ndim), dtype=torch.float64, device=self.device)
-            l = torch.empty((need, self.nwalkers), dtype=torch.float64, device=self.device)
+            c = torch.empty((need, nw, self.ndim), dtype=torch.float64, device=self.device)
+            l = torch.empty((need, nw), dtype=torch.float64, device=self.device)
             c[:self._nstored] = self._chain[:self._nstored]
             l[:self._nstored] = self._chain_lp[:self._nstored]
             self._chain, self._chain_lp = c, l
@@ -533,10 +542,13 @@ def _generateInitPars(mcmc, fit, rng=None):
     return p0[:walks]
 
 
-def mcmc_run(mcmc, fit, nburn, nsteps, nthin=1, autorefit=True, minfrac=0.2, minimprove=0.01, max_prefit=None):
+def mcmc_run(mcmc, fit, nburn, nsteps, nthin=1, autorefit=True, minfrac=0.2, minimprove=0.01, max_prefit=None,
+             prefit_iterations=1000):
     """MCMC execution with the reference's schedule (``joxsz_funcs.py:572-635``): preliminary 1000-iteration
     rounds repeated while the best log-probability improves, burn-in, then the stored chain.
-    ``max_prefit`` optionally bounds the number of preliminary rounds (the reference's loop is unbounded)."""
+    ``max_prefit`` optionally bounds the number of preliminary rounds (the reference's loop is unbounded) and
+    ``prefit_iterations`` their length (1000 upstream).  With ``chain_shard`` the best log-probability of a round is
+    reduced over the ranks, and the restart ensemble is the sampler's full current state."""
     eng = mcmc.engine
     bestprob = float(eng(np.asarray(fit.thawedParVals(), dtype=np.float64)))
     newlike = bestprob
@@ -545,10 +557,16 @@ def mcmc_run(mcmc, fit, nburn, nsteps, nthin=1, autorefit=True, minfrac=0.2, min
     rounds = 0
     while newlike >= bestprob:
         bestprob = newlike
-        for _ in mcmc.sample(p0, thin=500, iterations=1000, progress=False):
+        for _ in mcmc.sample(p0, thin=max(prefit_iterations // 2, 1), iterations=prefit_iterations, progress=False):
             pass
-        newlike = float(mcmc.backend.get_log_prob()[-1, :].max())
-        p0 = mcmc.backend.get_chain()[-1, :, :]
+        if getattr(mcmc, "chain_shard", False):
+            # a sharded chain holds this rank's walkers only; the last stored sample is the current ensemble (an even
+            # round length is stored at its last iteration), which every rank holds in full
+            newlike = float(mcmc.log_prob_host().max())
+            p0 = mcmc.coords_host()
+        else:
+            newlike = float(mcmc.backend.get_log_prob()[-1, :].max())
+            p0 = mcmc.backend.get_chain()[-1, :, :]
         mcmc.backend.reset(mcmc.nwalkers, len(fit.thawedParVals()))
         rounds += 1
         if max_prefit is not None and rounds >= max_prefit:
@@ -556,7 +574,7 @@ def mcmc_run(mcmc, fit, nburn, nsteps, nthin=1, autorefit=True, minfrac=0.2, min
     print('Burn-in period')
     for _ in mcmc.sample(p0, thin=max(nburn // 2, 1), iterations=nburn, progress=False):
         pass
-    p1 = mcmc.backend.get_chain()[-1, :, :]
+    p1 = mcmc.backend.get_chain()[-1, :, :] if not getattr(mcmc, "chain_shard", False) else mcmc.coords_host()
     mcmc.backend.reset(mcmc.nwalkers, len(fit.thawedParVals()))
     print('Starting sampling')
     for _ in mcmc.sample(p1, thin=nthin, iterations=nsteps, progress=False):

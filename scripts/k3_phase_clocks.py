@@ -59,7 +59,17 @@ if __name__ == "__main__":
     nfin = int(torch.isfinite(ll).sum()) if hasattr(ll, "sum") else int(np.isfinite(ll).sum())
     names = ["A0 synth", "A1 rows", "B cols", "C rows+store"]
     tot = sum(out[i] for i in range(4))
-    print(f"walkers {W} (finite {nfin}), {n} launches; cycles per evaluated walker (thread 0 of its CTA):")
-    for i, nm in enumerate(names):
-        print(f"  {nm:10s} {out[i] / (n * W):10.0f}  {100.0 * out[i] / tot:5.1f} %")
-    print(f"  total      {tot / (n * W):10.0f}")
+    if tot:
+        print(f"k3_szmap_kernel: walkers {W} (finite {nfin}), {n} launches; cycles per evaluated walker (thread 0 of its CTA):")
+        for i, nm in enumerate(names):
+            print(f"  {nm:10s} {out[i] / (n * W):10.0f}  {100.0 * out[i] / tot:5.1f} %")
+        print(f"  total      {tot / (n * W):10.0f}")
+    # warp-specialised kernel (k3w_szmap.cu): thread 0 of the F group and thread 0 of the M group
+    lib.jx_debug_k3w_clocks.argtypes = [C.POINTER(C.c_ulonglong)]
+    lib.jx_debug_k3w_clocks(out)
+    if sum(out):
+        print(f"k3w_szmap_kernel: walkers {W}, {n + 3} launches; cycles per walker")
+        nm = ["F A0 synth", "F A1 rows", "M B compute", "M B write-back", "F wait bdone", "F C rows+store", "M wait full", "-"]
+        for i in range(7):
+            print(f"  {nm[i]:16s} {out[i] / ((n + 3) * W):10.0f}")
+        print(f"  F total {sum(out[i] for i in (0, 1, 4, 5)) / ((n + 3) * W):10.0f}   M total {sum(out[i] for i in (2, 3, 6)) / ((n + 3) * W):10.0f}")

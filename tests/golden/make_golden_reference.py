@@ -96,23 +96,35 @@ def build_reference_fit(ref, mb, data_dir):
 
 
 def main():
+    """``--real-deps``: use the really installed PyAbel / mbproj2 / astropy instead of the restated stand-ins wherever
+    they import (refstubs.real_deps_available), write ``cl1226_golden_realdeps.npz`` next to the committed goldens and
+    print the largest difference of every recorded quantity against them -- the check that pins the third-party
+    boundary, for a maintainer whose machine has those packages (the build container has none of them)."""
     from joxsz_b200 import cluster
     from joxsz_b200.synthetic import synthetic_countrate_tables, draw_parameters
 
+    real_deps = "--real-deps" in sys.argv
     data_dir = os.path.join(refstubs.REFERENCE_DIR, "data")
-    # 1. raw inputs fixture (this repo's readers; checked against the reference's readers below)
-    inp = cluster.load_cl1226_files(data_dir)
-    cluster.save_inputs_npz(inp, os.path.join(HERE, "cl1226_inputs.npz"))
+    if real_deps:
+        have = refstubs.real_deps_available()
+        print("really installed:", have)
+        if not (have["abel"] or have["mbproj2"]):
+            raise SystemExit("--real-deps: neither PyAbel nor mbproj2 is importable here; nothing to pin")
+    else:
+        # 1. raw inputs fixture (this repo's readers; checked against the reference's readers below)
+        inp = cluster.load_cl1226_files(data_dir)
+        cluster.save_inputs_npz(inp, os.path.join(HERE, "cl1226_inputs.npz"))
 
     # 2. the reference's own code
-    ref, mb = refstubs.import_reference()
+    ref, mb = refstubs.import_reference(real_deps)
     mb.fit.debugfit = False
     fit, bandEs = build_reference_fit(ref, mb, data_dir)
     ctr = fit.data.annuli.ctrate
     tables = synthetic_countrate_tables([(b.emin_keV, b.emax_keV) for b in fit.data.bands], ctr.Tlogvals)
     for band, (t0, t1) in zip(fit.data.bands, tables):
-        ctr.setTables(ctr.makeKey(band.rmf, band.arf, band.emin_keV, band.emax_keV, fit.model.NH_1022pcm2,
-                                  ctr.cosmo.z), t0, t1)
+        # key layout documented by the reference's own addCountCache (joxsz_funcs.py:652-681)
+        key = (band.emin_keV, band.emax_keV, ctr.cosmo.z, fit.model.NH_1022pcm2, band.rmf, band.arf)
+        ctr.ctcache[key] = (np.asarray(t0, dtype=np.float64), np.asarray(t1, dtype=np.float64))
 
     thawed = list(fit.thawed)
     default_theta = np.array(fit.thawedParVals(), dtype=np.float64)
@@ -147,8 +159,22 @@ def main():
             out["cint"][w] = fit.get_sz_like(output="integ")
     sz.calc_integ = False
     print("finite ll:", int(np.isfinite(out["ll"]).sum()), "of", W, " ll[0] =", out["ll"][0])
+    outname = "cl1226_golden_realdeps.npz" if real_deps else "cl1226_golden.npz"
+    if real_deps:
+        old = np.load(os.path.join(HERE, "cl1226_golden.npz"))
+        print("largest differences against the committed goldens (third-party stand-ins):")
+        for k, v in out.items():
+            if k in old.files:
+                a, b = np.asarray(v, float), np.asarray(old[k], float)
+                fin = np.isfinite(a) & np.isfinite(b)
+                same_mask = bool(np.array_equal(np.isfinite(a), np.isfinite(b)))
+                scale = np.max(np.abs(b[fin])) if fin.any() else 1.0
+                print(f"  {k:12s} max |d| = {np.max(np.abs(a[fin] - b[fin])) if fin.any() else 0.0:.3e}"
+                      f"  (/ max |golden| = {np.max(np.abs(a[fin] - b[fin])) / scale if fin.any() else 0.0:.3e})"
+                      f"  finite mask equal: {same_mask}")
     np.savez_compressed(
-        os.path.join(HERE, "cl1226_golden.npz"), thawed=np.array(thawed), thetas=thetas,
+        os.path.join(HERE, outname), deps_mode=np.array(sorted(f"{k}={v}" for k, v in refstubs.MODE.items())),
+        thawed=np.array(thawed), thetas=thetas,
         r_pp=sz.r_pp, radius=sz.radius, sep=np.array(sz.sep), kpc_as=np.array(sz.kpc_as),
         beam_2d=sz.beam_2d, filtering=sz.filtering, d_mat_row=sz.d_mat[sz.sep],
         midpt_kpc=fit.data.annuli.midpt_kpc, projvols_cm3=fit.data.annuli.projvols_cm3,

@@ -23,7 +23,30 @@ def reference_available():
     return os.path.exists(os.path.join(REFERENCE_DIR, "joxsz_funcs.py"))
 
 
-def _install_stubs():
+def real_deps_available():
+    """Which of the third-party packages the reference imports are really installed (never true in the build
+    container; a maintainer's machine may have them)."""
+    import importlib.util
+    out = {}
+    for name in ("abel", "mbproj2", "astropy", "h5py"):
+        try:
+            out[name] = importlib.util.find_spec(name) is not None
+        except (ImportError, ValueError):
+            out[name] = False
+    return out
+
+
+#: filled by _install_stubs: {"abel": "real" | "stub", "mbproj2": ..., "astropy": ..., "h5py": ...}
+MODE = {}
+
+
+def _install_stubs(real_deps=False):
+    """``real_deps=True``: every package of ``real_deps_available()`` that is installed is used as it is (PyAbel's own
+    ``direct_transform``, mbproj2's own ``Fit`` / ``Band`` / ``CountRate`` ...) and only the missing ones are stubbed;
+    the goldens generated that way pin the third-party boundary itself (make_golden_reference.py --real-deps)."""
+    have = real_deps_available() if real_deps else {}
+    MODE.clear()
+    MODE.update({k: ("real" if have.get(k) else "stub") for k in ("abel", "mbproj2", "astropy", "h5py")})
     here = os.path.dirname(os.path.abspath(__file__))
     root = os.path.abspath(os.path.join(here, "..", ".."))
     if root not in sys.path:
@@ -42,14 +65,46 @@ def _install_stubs():
         def __getitem__(self, key):
             return _HDU(self._rows)
 
-    fits = types.ModuleType("astropy.io.fits")
-    fits.open = lambda filename: _HDUList(filename)
-    astropy = types.ModuleType("astropy")
-    astropy_io = types.ModuleType("astropy.io")
-    astropy.io = astropy_io
-    astropy_io.fits = fits
-    sys.modules.update({"astropy": astropy, "astropy.io": astropy_io, "astropy.io.fits": fits})
+    if MODE["astropy"] == "stub":
+        fits = types.ModuleType("astropy.io.fits")
+        fits.open = lambda filename: _HDUList(filename)
+        astropy = types.ModuleType("astropy")
+        astropy_io = types.ModuleType("astropy.io")
+        astropy.io = astropy_io
+        astropy_io.fits = fits
+        sys.modules.update({"astropy": astropy, "astropy.io": astropy_io, "astropy.io.fits": fits})
 
+    if MODE["mbproj2"] == "real":
+        import mbproj2 as real_mb
+        mb_out = real_mb
+    else:
+        mb_out = mbshim
+        _patch_shim_host_arithmetic(mbshim)
+        sys.modules["mbproj2"] = mbshim
+        sys.modules["mbproj2.physconstants"] = mbshim.physconstants
+
+    if MODE["abel"] == "stub":
+        abel = types.ModuleType("abel")
+        direct = types.ModuleType("abel.direct")
+
+        def direct_transform(fr, dr=None, r=None, direction="inverse", derivative=None, int_func=None,
+                             correction=True, backend="C", **kw):
+            assert direction == "forward" and backend == "Python" and r is not None
+            return orc.pyabel_direct_forward(fr, r)
+
+        direct.direct_transform = direct_transform
+        abel.direct = direct
+        sys.modules.update({"abel": abel, "abel.direct": direct})
+    if MODE["h5py"] == "stub":
+        sys.modules["h5py"] = types.ModuleType("h5py")
+
+    import scipy.integrate
+    if not hasattr(scipy.integrate, "simps"):
+        scipy.integrate.simps = scipy.integrate.simpson
+    return mb_out
+
+
+def _patch_shim_host_arithmetic(mbshim):
     # The product shim deliberately has no host arithmetic for the per-walker X-ray path; the reference's own
     # getLikelihood needs it, so numpy restatements of the three mbproj2 routines
     # are patched in for this run only.
@@ -87,31 +142,11 @@ def _install_stubs():
     mbshim.utils.cashLogLikelihood = _cashLogLikelihood
     mbshim.Fit.calcProfiles = _calcProfiles
 
-    sys.modules["mbproj2"] = mbshim
-    sys.modules["mbproj2.physconstants"] = mbshim.physconstants
-
-    abel = types.ModuleType("abel")
-    direct = types.ModuleType("abel.direct")
-
-    def direct_transform(fr, dr=None, r=None, direction="inverse", derivative=None, int_func=None,
-                         correction=True, backend="C", **kw):
-        assert direction == "forward" and backend == "Python" and r is not None
-        return orc.pyabel_direct_forward(fr, r)
-
-    direct.direct_transform = direct_transform
-    abel.direct = direct
-    sys.modules.update({"abel": abel, "abel.direct": direct})
-    sys.modules["h5py"] = types.ModuleType("h5py")
-
-    import scipy.integrate
-    if not hasattr(scipy.integrate, "simps"):
-        scipy.integrate.simps = scipy.integrate.simpson
-    return mbshim
 
 
-def import_reference():
+def import_reference(real_deps=False):
     """Returns (ref_module, mb) with the reference's joxsz_funcs loaded from /root/reference."""
-    mb = _install_stubs()
+    mb = _install_stubs(real_deps)
     spec = importlib.util.spec_from_file_location("ref_joxsz_funcs", os.path.join(REFERENCE_DIR, "joxsz_funcs.py"))
     ref = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(ref)
