@@ -382,7 +382,8 @@ def run_gpu_arm(args):
     eng = BatchedLikelihood(fit, max_walkers=max(W // world + 64, 1024) if world > 1 else W, device=local)
     p0 = ensemble(fit, W)
     sampler = EnsembleSampler(W, eng.ndim, eng, seed=1234, world_size=world, rank=rank,
-                              group=(dist.group.WORLD if world > 1 else None), graph=not args.no_graph)
+                              group=(dist.group.WORLD if world > 1 else None), graph=not args.no_graph,
+                              exchange=args.exchange)
     sampler.initialize(p0)
 
     def barrier():
@@ -558,7 +559,11 @@ def run_gpu_arm(args):
                 "timed_blocks": TIMED_BLOCKS, "block_ms_per_step": [b / args.steps for b in blocks],
                 "value_is": "median block", "warmup_extra_steps": extra_warm,
                 "acceptance_fraction": acc, "state_checksum": checksum,
-                "sampler": {"cuda_graph": sampler.graph_active, "graph_fallback_reason": sampler._graph_failed},
+                "sampler": {"cuda_graph": sampler.graph_active, "graph_fallback_reason": sampler._graph_failed,
+                            "exchange": ("none (1 rank)" if world == 1 else
+                                         "p2p: accept kernel stores into every rank's buffer over NVLink, flags, no collective"
+                                         if sampler._px is not None else "nccl all_gather_into_tensor per half-step"),
+                            "p2p_fallback_reason": sampler._px_failed},
                 "clocks": clk.summary(), "e2e": e2e, "e2e_numpy": e2e_numpy,
                 "gpu_launches": int(sampler.launches_per_step() * args.steps),
                 "gpu_launches_note": "kernels of libjoxsz_b200.so per timed block (K steps), replayed from one CUDA graph "
@@ -605,6 +610,8 @@ def main():
     ap.add_argument("--secondary-steps", type=int, default=3)
     ap.add_argument("--secondary-cpu-sample", type=int, default=32)
     ap.add_argument("--no-graph", action="store_true", help="launch the sampler iteration kernel by kernel")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N > 1: how the half-step results travel between the ranks (see EnsembleSampler)")
     args = ap.parse_args()
     global WORKLOAD
     WORKLOAD = args.workload

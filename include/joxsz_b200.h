@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define JX_ABI_VERSION 6
+#define JX_ABI_VERSION 7
 
 typedef enum jx_status {
     JX_OK = 0,
@@ -227,6 +227,23 @@ int jx_stretch_advance(uint64_t* iter_dev, uint64_t by, int32_t device, void* st
 int jx_stretch_scatter(double* coords, double* lp, int32_t* naccept, const int32_t* perm, int32_t nall,
                        int32_t ndim, int32_t split, const double* packed_all, int32_t ns, int32_t device,
                        void* stream);
+/* accept fused with the exchange over peer memory (NVLink / NVSwitch), replacing accept + all-gather: every rank
+ * holds a buffer packed_all [2][world * per0][ndim + 2] and flags [2][world] (uint64, zero-initialised) that all ranks
+ * of the node can address (e.g. torch symmetric memory); `peer_packed` / `peer_flags` are HOST arrays of the `world`
+ * device addresses, in rank order.  The kernel writes this rank's rows (slice entry i -> row rank * per0 + i of
+ * buffer `split`) into every rank's packed_all and then stores the epoch `iteration + 1` into flags[split][rank] of
+ * every rank with release semantics at system scope.  `done` is a zero-initialised device counter owned by the caller.
+ * scatter_p2p waits until all `world` flags of buffer `split` reach the epoch and then applies the local copy (rank
+ * g's rows are r = g * per .. in half-step order).  emcee semantics are those of jx_stretch_accept / _scatter. */
+int jx_stretch_accept_p2p(const double* coords, const double* lp, const int32_t* perm, int32_t nall, int32_t ndim,
+                          int32_t split, int32_t r_first, int32_t r_count, const double* prop, const double* lp_new,
+                          const double* factor, uint64_t seed, uint64_t iteration, const uint64_t* iter_dev,
+                          const uint64_t* peer_packed, const uint64_t* peer_flags, int32_t world, int32_t rank,
+                          int32_t per0, uint32_t* done, int32_t device, void* stream);
+int jx_stretch_scatter_p2p(double* coords, double* lp, int32_t* naccept, const int32_t* perm, int32_t nall,
+                           int32_t ndim, int32_t split, const double* packed_local, const uint64_t* flags_local,
+                           int32_t ns, int32_t world, int32_t per, int32_t per0, uint64_t iteration,
+                           const uint64_t* iter_dev, int32_t device, void* stream);
 
 /* ---- measurement helpers (bench.py) */
 enum jx_stage { JX_ST_PROFILES = 0, JX_ST_PROJECT, JX_ST_SZMAP, JX_ST_XRAY, JX_ST_TAIL, JX_ST_FILTER, JX_NSTAGE };

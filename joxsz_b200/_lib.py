@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-JX_ABI_VERSION = 6
+JX_ABI_VERSION = 7
 JX_NPAR = 19
 JX_NSTAGE = 6
 STAGE_NAMES = ("profiles", "project", "szmap", "xray", "tail", "filter")
@@ -72,6 +72,11 @@ PROTOTYPES = {
     "jx_stretch_advance": (C.c_int, [_vp, C.c_uint64, C.c_int32, _vp]),
     "jx_stretch_scatter": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int32,
                                      C.c_int32, _vp]),
+    "jx_stretch_accept_p2p": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp,
+                                        _vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp,
+                                        C.c_int32, _vp]),
+    "jx_stretch_scatter_p2p": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_int32,
+                                         C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _vp, C.c_int32, _vp]),
     "jx_set_profiling": (C.c_int, [_vp, C.c_int32]),
     "jx_stage_times": (C.c_int, [_vp, _pd, C.POINTER(C.c_int64)]),
     "jx_build_info": (C.c_char_p, []),

@@ -95,7 +95,7 @@ void flush_stage_events(jx_handle* h) {
 }  // namespace
 
 extern "C" const char* jx_build_info(void) {
-    return "libjoxsz_b200 abi=" "6" " arch=sm_100a fp64 K1=profiles K2=dmma-project K3=fft256-szmap(smem)|fft512/1024-szmap(L2) K7=dmma-filter K4=xray K5=tail";
+    return "libjoxsz_b200 abi=" "7" " arch=sm_100a fp64 K1=profiles K2=dmma-project K3=fft256-szmap(smem)|fft512/1024-szmap(L2) K7=dmma-filter K4=xray K5=tail";
 }
 
 extern "C" const char* jx_last_error(const jx_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }

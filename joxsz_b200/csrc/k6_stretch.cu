@@ -100,6 +100,88 @@ __global__ void k6_scatter_kernel(double* __restrict__ coords, double* __restric
     if (naccept && o[ndim + 1] != 0.0) naccept[k] += 1;
 }
 
+// ---- accept fused with the exchange: every rank writes its rows straight into the packed_all buffer of EVERY rank
+// (peer memory over NVLink / NVSwitch), then raises one flag per peer; the scatter kernel of a rank waits for the flags
+// of all ranks and reads its local copy.  No collective launch, no host involvement: the half-step's only
+// communication is these stores.  Buffers are double-buffered by `split`: a rank can run at most one half-step ahead
+// of a peer (its next scatter waits for that peer's accept), so the buffer of half-step k is never overwritten
+// before every rank's scatter of k has read it.
+constexpr int JX_MAX_PEERS = 16;
+struct k6_peers {
+    double* packed[JX_MAX_PEERS];     // [2][world * per0][ndim + 2] on every rank
+    uint64_t* flags[JX_MAX_PEERS];    // [2][world] epochs on every rank
+};
+
+JX_D void st_release_sys(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+JX_D uint64_t ld_acquire_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void k6_accept_p2p_kernel(const double* __restrict__ coords, const double* __restrict__ lp,
+                                     const int32_t* __restrict__ perm, int ndim, int split, int r_first, int r_count,
+                                     const double* __restrict__ prop, const double* __restrict__ lp_new,
+                                     const double* __restrict__ factor, uint64_t seed, uint64_t iteration,
+                                     const uint64_t* __restrict__ iter_dev, k6_peers peers, int world, int rank, int per0,
+                                     unsigned int* __restrict__ done) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    iteration = effective_iteration(iteration, iter_dev);
+    if (i < r_count) {
+        const int k = perm[2 * (r_first + i) + split];
+        philox4 r = philox4x32_10((uint32_t)k, (uint32_t)iteration, (uint32_t)(iteration >> 32),
+                                  stream_word(PURPOSE_ACCEPT, split), (uint32_t)seed, (uint32_t)(seed >> 32));
+        const double lnu = log(u01(r.v[0], r.v[1]));
+        const double lnpdiff = factor[i] + lp_new[i] - lp[k];
+        const bool acc = lnpdiff > lnu;
+        const size_t row = ((size_t)split * world * per0 + (size_t)rank * per0 + i) * (ndim + 2);
+        const double* src = acc ? prop + (size_t)i * ndim : coords + (size_t)k * ndim;
+        const double lpv = acc ? lp_new[i] : lp[k], av = acc ? 1.0 : 0.0;
+        for (int p = 0; p < world; ++p) {
+            double* o = peers.packed[p] + row;
+            for (int d = 0; d < ndim; ++d) o[d] = src[d];
+            o[ndim] = lpv;
+            o[ndim + 1] = av;
+        }
+    }
+    __threadfence_system();                    // this thread's rows are visible to every GPU before the CTA reports
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x - 1) {           // last CTA of the grid: every row of this rank has been written
+            *done = 0u;
+            __threadfence_system();
+            for (int p = 0; p < world; ++p)
+                st_release_sys(peers.flags[p] + (size_t)split * world + rank, iteration + 1);
+        }
+    }
+}
+
+// rows of the half-step: r = 0..ns-1 in the order of the ranks' slices; rank g's slice starts at g * per in r and at
+// g * per0 in the buffer (per <= per0: the second colour of an odd ensemble has one walker fewer)
+__global__ void k6_scatter_p2p_kernel(double* __restrict__ coords, double* __restrict__ lp, int32_t* __restrict__ naccept,
+                                      const int32_t* __restrict__ perm, int ndim, int split,
+                                      const double* __restrict__ packed_local, const uint64_t* __restrict__ flags_local,
+                                      int ns, int world, int per, int per0, uint64_t iteration,
+                                      const uint64_t* __restrict__ iter_dev) {
+    iteration = effective_iteration(iteration, iter_dev);
+    if (threadIdx.x < world) {
+        const uint64_t* f = flags_local + (size_t)split * world + threadIdx.x;
+        while (ld_acquire_sys(f) < iteration + 1) __nanosleep(64);
+    }
+    __syncthreads();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= ns) return;
+    const int g = r / per, off = r - g * per;
+    const int k = perm[2 * r + split];
+    const double* o = packed_local + ((size_t)split * world * per0 + (size_t)g * per0 + off) * (ndim + 2);
+    for (int d = 0; d < ndim; ++d) coords[(size_t)k * ndim + d] = __ldcv(o + d);
+    lp[k] = __ldcv(o + ndim);
+    if (naccept && __ldcv(o + ndim + 1) != 0.0) naccept[k] += 1;
+}
+
 // sort keys of the colouring permutation: 64 random bits per walker (ties are broken by the stable sort)
 __global__ void k6_shuffle_keys_kernel(uint64_t* __restrict__ keys, int32_t* __restrict__ vals, int nall, uint64_t seed,
                                        uint64_t iteration, const uint64_t* __restrict__ iter_dev) {
@@ -193,5 +275,44 @@ extern "C" int jx_stretch_advance(uint64_t* iter_dev, uint64_t by, int32_t devic
     if (!iter_dev) return JX_ERR_INVALID;
     if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
     k6_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(iter_dev, by);
+    return cudaGetLastError() == cudaSuccess ? JX_OK : JX_ERR_CUDA;
+}
+
+extern "C" int jx_stretch_accept_p2p(const double* coords, const double* lp, const int32_t* perm, int32_t nall,
+                                     int32_t ndim, int32_t split, int32_t r_first, int32_t r_count, const double* prop,
+                                     const double* lp_new, const double* factor, uint64_t seed, uint64_t iteration,
+                                     const uint64_t* iter_dev, const uint64_t* peer_packed, const uint64_t* peer_flags,
+                                     int32_t world, int32_t rank, int32_t per0, uint32_t* done, int32_t device,
+                                     void* stream) {
+    if (!coords || !lp || !perm || !peer_packed || !peer_flags || !done || ndim < 1) return JX_ERR_INVALID;
+    if (world < 1 || world > JX_MAX_PEERS || rank < 0 || rank >= world || per0 < 1 || r_count > per0) return JX_ERR_INVALID;
+    if (r_count > 0 && (!prop || !lp_new || !factor)) return JX_ERR_INVALID;
+    if (!slice_ok(nall, split, r_first, r_count)) return JX_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
+    k6_peers peers;
+    for (int p = 0; p < JX_MAX_PEERS; ++p) {
+        peers.packed[p] = p < world ? reinterpret_cast<double*>(peer_packed[p]) : nullptr;
+        peers.flags[p] = p < world ? reinterpret_cast<uint64_t*>(peer_flags[p]) : nullptr;
+        if (p < world && (!peers.packed[p] || !peers.flags[p])) return JX_ERR_INVALID;
+    }
+    const int grid = r_count > 0 ? (r_count + 127) / 128 : 1;      // a rank without rows still raises its flags
+    k6_accept_p2p_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(coords, lp, perm, ndim, split, r_first, r_count, prop,
+                                                                 lp_new, factor, seed, iteration, iter_dev, peers, world,
+                                                                 rank, per0, done);
+    return cudaGetLastError() == cudaSuccess ? JX_OK : JX_ERR_CUDA;
+}
+
+extern "C" int jx_stretch_scatter_p2p(double* coords, double* lp, int32_t* naccept, const int32_t* perm, int32_t nall,
+                                      int32_t ndim, int32_t split, const double* packed_local, const uint64_t* flags_local,
+                                      int32_t ns, int32_t world, int32_t per, int32_t per0, uint64_t iteration,
+                                      const uint64_t* iter_dev, int32_t device, void* stream) {
+    if (!coords || !lp || !perm || !packed_local || !flags_local || ndim < 1 || split < 0 || split > 1) return JX_ERR_INVALID;
+    if (world < 1 || world > JX_MAX_PEERS || per < 1 || per > per0) return JX_ERR_INVALID;
+    if (ns != (nall - split + 1) / 2 || (size_t)per * world < (size_t)ns) return JX_ERR_INVALID;
+    if (ns == 0) return JX_OK;
+    if (cudaSetDevice(device) != cudaSuccess) return JX_ERR_CUDA;
+    k6_scatter_p2p_kernel<<<(ns + 127) / 128, 128, 0, (cudaStream_t)stream>>>(coords, lp, naccept, perm, ndim, split,
+                                                                               packed_local, flags_local, ns, world, per,
+                                                                               per0, iteration, iter_dev);
     return cudaGetLastError() == cudaSuccess ? JX_OK : JX_ERR_CUDA;
 }

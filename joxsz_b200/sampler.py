@@ -96,6 +96,49 @@ class CudaStretchOps:
                                          _ptr(packed_all), ns, self.index, self._stream())
         _lib.check(rc)
 
+    # ---- accept + exchange over peer memory (no collective launch)
+    def accept_p2p(self, coords, lp, perm, split, r_first, r_count, prop, lp_new, factor, seed, iteration, px):
+        nall, ndim = coords.shape
+        rc = self.lib.jx_stretch_accept_p2p(_ptr(coords), _ptr(lp), _ptr(perm), nall, ndim, split, r_first, r_count,
+                                            _ptr(prop), _ptr(lp_new), _ptr(factor), C.c_uint64(seed),
+                                            C.c_uint64(iteration), self._iter_ptr(), px.peer_packed, px.peer_flags,
+                                            px.world, px.rank, px.per0, _ptr(px.done), self.index, self._stream())
+        _lib.check(rc)
+
+    def scatter_p2p(self, coords, lp, naccept, perm, split, ns, per, iteration, px):
+        nall, ndim = coords.shape
+        rc = self.lib.jx_stretch_scatter_p2p(_ptr(coords), _ptr(lp), _ptr(naccept), _ptr(perm), nall, ndim, split,
+                                             _ptr(px.packed), _ptr(px.flags), ns, px.world, per, px.per0,
+                                             C.c_uint64(iteration), self._iter_ptr(), self.index, self._stream())
+        _lib.check(rc)
+
+
+class PeerExchange:
+    """Buffers of the fused accept + exchange: ``packed`` [2, world * per0, ndim + 2] float64 and ``flags`` [2, world]
+    int64 in torch symmetric memory (every rank of the node can store into every rank's copy over NVLink), and the
+    host arrays of the peers' device addresses the kernels take."""
+
+    def __init__(self, world, rank, per0, ndim, device, group):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank, self.per0 = world, rank, per0
+        self.packed = symm.empty((2 * world * per0 * (ndim + 2),), dtype=torch.float64, device=device)
+        self.flags = symm.empty((2 * world,), dtype=torch.int64, device=device)
+        self.packed.zero_()
+        self.flags.zero_()
+        self.done = torch.zeros((1,), dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        group = group if group is not None else dist.group.WORLD
+        hp = symm.rendezvous(self.packed, group)
+        hf = symm.rendezvous(self.flags, group)
+        self._handles = (hp, hf)
+        self.peer_packed = (C.c_uint64 * world)(*[int(p) for p in hp.buffer_ptrs])
+        self.peer_flags = (C.c_uint64 * world)(*[int(p) for p in hf.buffer_ptrs])
+        if int(hp.buffer_ptrs[rank]) != self.packed.data_ptr() or int(hf.buffer_ptrs[rank]) != self.flags.data_ptr():
+            raise RuntimeError("symmetric memory: local buffer address mismatch")
+        dist.barrier(group=group)             # every rank's flags are zero before anyone stores into them
+        torch.cuda.synchronize(device)
+
 
 def shard_bounds(ns: int, world: int, rank: int):
     """Slice of the ``ns`` active walkers of a half-step handled by ``rank``: (per, r_first, r_count).
@@ -141,7 +184,7 @@ class EnsembleSampler:
     """
 
     def __init__(self, nwalkers, ndim, log_prob_fn, pool=None, backend=None, a=2.0, seed=None, world_size=1,
-                 rank=0, group=None, ops=None, device=None, vectorize=True, moves=None, graph=None, chain_shard=False):
+                 rank=0, group=None, ops=None, device=None, vectorize=True, moves=None, graph=None, chain_shard=False, exchange="auto"):
         if nwalkers < 2 * ndim:
             raise ValueError("The number of walkers needs to be at least twice the dimension of the problem")
         if moves is not None:
@@ -185,6 +228,15 @@ class EnsembleSampler:
         lo = (self.nwalkers * self.rank) // self.world if self.chain_shard else 0
         hi = (self.nwalkers * (self.rank + 1)) // self.world if self.chain_shard else self.nwalkers
         self.chain_walkers = (lo, hi)
+        #: how the half-step results travel between the ranks: "p2p" = the accept kernel stores its rows into every rank's
+        #: buffer over NVLink peer memory and the scatter kernel waits on flags (no collective launch); "nccl" = accept,
+        #: then one all_gather_into_tensor; "auto" = p2p when the CUDA kernels run on > 1 rank and torch symmetric
+        #: memory can be set up, else nccl
+        if exchange not in ("auto", "p2p", "nccl"):
+            raise ValueError("exchange must be 'auto', 'p2p' or 'nccl'")
+        self.exchange = exchange
+        self._px = None
+        self._px_failed = None
         self._graph = None
         self._graph_failed = None
         self.eager_only = False               # True: launch kernel by kernel even if a graph exists (per-kernel timers)
@@ -230,6 +282,20 @@ class EnsembleSampler:
         self._pa_buf = None
         if self.world > 1:
             self._pa_buf = torch.zeros((per * self.world, nd + 2), dtype=f64, device=dev)
+        if self.world > 1 and self.exchange != "nccl" and isinstance(self.ops, CudaStretchOps):
+            try:
+                self._px = PeerExchange(self.world, self.rank, per, nd, dev, self.group)
+            except Exception as e:
+                self._px_failed = f"{type(e).__name__}: {e}"
+                if self.exchange == "p2p":
+                    raise
+        if self.world > 1 and isinstance(self.ops, CudaStretchOps):
+            # every rank must take the same path: p2p only if every rank could set it up
+            import torch.distributed as dist
+            ok = torch.tensor([1 if self._px is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                self._px = None
         if self.use_graph:
             self._iter_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
             self._perm_g = torch.zeros((W,), dtype=torch.int32, device=dev)
@@ -293,6 +359,14 @@ class EnsembleSampler:
                 prop = self._prop[:count]
                 self.ops.propose(self._coords, perm, split, first, count, self.a, self.seed, it, prop, self._factor)
                 self.engine.loglike_device(prop, out=self._lpnew[:count])
+            if self._px is not None:
+                # accept + exchange in one kernel: rows go straight into every rank's buffer over NVLink
+                self.ops.accept_p2p(self._coords, self._lp, perm, split, first, count, self._prop, self._lpnew,
+                                    self._factor, self.seed, it, self._px)
+                self.ops.scatter_p2p(self._coords, self._lp, self._naccept, perm, split, ns, per, it, self._px)
+                self.aux_launches += 2
+                continue
+            if count:
                 self.ops.accept(self._coords, self._lp, perm, split, first, count, prop, self._lpnew,
                                 self._factor, self.seed, it, self._packed)
             if self.world > 1:

@@ -100,3 +100,51 @@ def test_filter_identity_and_nan_quirk(cl1226_oracle):
     p["P_0"] = float("nan")
     with np.errstate(all="ignore"):
         assert orc.sz_stages(p, s)["chisq"] == 0.0
+
+
+def test_abel_operator_is_pinned_to_its_discretisation():
+    """Tight KAT for the PyAbel direct transform as the reference calls it (joxsz_funcs.py:457): an independent scalar
+    restatement of the discretisation -- first cell integrated exactly for the piecewise-linear integrand (here by
+    adaptive quadrature of the substituted, smooth integrand), trapezoid rule on f(r)/sqrt(r^2 - y^2) beyond it, last
+    point zero -- must agree with the oracle and with the dense operator the CUDA path uses to 1e-12.  The closed-form
+    pairs above only bound the method's own discretisation error (1e-2 .. 1e-3): a different but convergent variant
+    would pass them and fail this one."""
+    from scipy.integrate import quad
+    from joxsz_b200 import operators as ops
+    rng = np.random.default_rng(5)
+    r = 16.00139 * np.arange(1, 61)
+    pp = np.exp(-r / 300.0) * (1 + 0.1 * rng.standard_normal(r.size))
+    f = 2.0 * r * pp
+    n = r.size
+    want = np.zeros(n)
+    for i in range(n - 1):
+        y = r[i]
+        slope = (f[i + 1] - f[i]) / (r[i + 1] - r[i])
+        # integral over [r_i, r_{i+1}] of (f_i + slope (r - r_i)) / sqrt(r^2 - y^2) dr with r = y cosh(t)
+        first, _ = quad(lambda t: f[i] + slope * (y * math.cosh(t) - y), 0.0, math.acosh(r[i + 1] / y),
+                        epsabs=0, epsrel=2e-14)
+        g = f[i + 1:] / np.sqrt(r[i + 1:] ** 2 - y * y)
+        trap = float(np.sum(0.5 * (g[1:] + g[:-1]) * np.diff(r[i + 1:])))
+        if i == n - 2:
+            # edge artefact of PyAbel's code, kept because the reference calls that code: the half-weight it takes off
+            # the spike sample j = i + 1 is computed from the two intervals around it, and the last sample has only
+            # one -- a quarter of the spike trapezoid survives in the second-to-last output
+            trap += 0.25 * g[0] * (r[i + 1] - r[i])
+        want[i] = first + trap
+    got = orc.pyabel_direct_forward(pp, r)
+    scale = np.max(np.abs(want))
+    assert np.max(np.abs(got - want)) < 1e-12 * scale
+    assert got[-1] == 0.0
+    A = ops.abel_forward_matrix(r)
+    assert np.max(np.abs(A @ pp - want)) < 1e-12 * scale
+    # convergence order of this discretisation against the closed form: the trapezoid rule meets the inverse-square-root
+    # behaviour next to the exactly integrated first cell, so halving the step divides the error by ~sqrt(2), not 4
+    s = 400.0
+    errs = []
+    for h in (16.0, 8.0, 4.0):
+        rr = h * np.arange(1, int(5000 / h) + 1)
+        F = orc.pyabel_direct_forward(np.exp(-(rr / s) ** 2), rr)
+        exact = s * math.sqrt(math.pi) * np.exp(-(rr / s) ** 2)
+        k = int(round(160.0 / h)) - 1                      # the sample at r = 160
+        errs.append(abs(F[k] - exact[k]))
+    assert 1.2 < errs[0] / errs[1] < 1.7 and 1.2 < errs[1] / errs[2] < 1.7

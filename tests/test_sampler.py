@@ -319,7 +319,7 @@ def test_graph_replay_equals_eager_steps(cl1226_fit):
     eng.close()
 
 
-def _nccl_worker(rank, world, port, W, steps, graph, q):
+def _nccl_worker(rank, world, port, W, steps, graph, exchange, q):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -336,21 +336,25 @@ def _nccl_worker(rank, world, port, W, steps, graph, q):
     fit, _ = cluster.build_fit(inp, savedir=None)
     eng = BatchedLikelihood(fit, max_walkers=256, device=rank)
     p0 = draw_parameters(fit.thawed, n=W, seed=8, spread=0.01)
-    s = EnsembleSampler(W, eng.ndim, eng, seed=5, world_size=world, rank=rank, group=dist.group.WORLD, graph=graph)
+    s = EnsembleSampler(W, eng.ndim, eng, seed=5, world_size=world, rank=rank, group=dist.group.WORLD, graph=graph,
+                        exchange=exchange)
     s.initialize(p0)
     for _ in range(steps):
         s.step()
-    q.put((rank, s.coords_host(), s.log_prob_host(), s.acceptance_fraction, s.graph_active, s._graph_failed))
+    q.put((rank, s.coords_host(), s.log_prob_host(), s.acceptance_fraction, s.graph_active, s._graph_failed,
+           s._px is not None))
     dist.barrier()
     eng.close()
     dist.destroy_process_group()
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
 @pytest.mark.parametrize("graph", [False, True])
-def test_two_nccl_ranks_reproduce_single_gpu_chain(cl1226_fit, graph):
-    """Hardware proof of rank-count invariance: 2 processes / 2 GPUs over NCCL end with the ensemble of the 1-GPU run,
-    bit for bit (eager launches and the captured graph with the all-gathers inside)."""
+def test_two_nccl_ranks_reproduce_single_gpu_chain(cl1226_fit, graph, exchange):
+    """Hardware proof of rank-count invariance: 2 processes / 2 GPUs end with the ensemble of the 1-GPU run, bit for
+    bit -- eager launches and the captured graph, with the NCCL all-gather and with the accept kernel storing its rows
+    into the peer's buffer over NVLink (odd half-ensembles: 35 walkers per colour over 2 ranks)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
@@ -365,15 +369,16 @@ def test_two_nccl_ranks_reproduce_single_gpu_chain(cl1226_fit, graph):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, W, steps, graph, q)) for r in range(world)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, W, steps, graph, exchange, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    for rank, coords, lp, acc, active, failed in res:
+    for rank, coords, lp, acc, active, failed, p2p in res:
         assert active == graph, failed
+        assert p2p == (exchange == "p2p")
         assert np.array_equal(coords, ref.coords_host())
         assert np.array_equal(lp, ref.log_prob_host())
         assert np.array_equal(acc, ref.acceptance_fraction)
