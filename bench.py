@@ -265,6 +265,11 @@ def fp64_lane_ops(pk):
     return synth + rows + ycols
 
 
+def note(msg):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def time_blocks(step_fn, steps, blocks, barrier, reduce_max):
     import torch
     out = []
@@ -311,20 +316,25 @@ def run_secondary(name, world, rank, local, dist, args, barrier, reduce_max):
     from joxsz_b200.batched import BatchedLikelihood
     from joxsz_b200.sampler import EnsembleSampler
     t_build = time.perf_counter()
+    note(f"secondary {name}: building the cluster")
     fit = build_cluster(name)
     Wn = args.secondary_walkers * world
     eng = BatchedLikelihood(fit, max_walkers=Wn // world + 64, device=local)
     sampler = EnsembleSampler(Wn, eng.ndim, eng, seed=4321, world_size=world, rank=rank,
                               group=(dist.group.WORLD if world > 1 else None))
+    note(f"secondary {name}: engine ready, initialising {Wn} walkers")
     sampler.initialize(ensemble(fit, Wn, seed=20260105))
     t_build = time.perf_counter() - t_build
+    note(f"secondary {name}: set-up {t_build:.1f} s, stepping")
     steps = args.secondary_steps
     for _ in range(3):
         sampler.step()
     blocks = time_blocks(sampler.step, steps, 3, barrier, reduce_max)
     ms = sorted(blocks)[len(blocks) // 2]
     chk = state_checksum(sampler)
+    note(f"secondary {name}: {ms / steps:.2f} ms / step, profiling pass")
     stages = profile_pass(eng, sampler, 2)
+    note(f"secondary {name}: CPU sample")
     out = None
     if rank == 0:
         pk = eng.packed
@@ -377,9 +387,11 @@ def run_gpu_arm(args):
     from joxsz_b200.batched import BatchedLikelihood
     from joxsz_b200.sampler import EnsembleSampler
 
+    note("building the cluster")
     fit = build_cluster()
     W = args.walkers
     eng = BatchedLikelihood(fit, max_walkers=max(W // world + 64, 1024) if world > 1 else W, device=local)
+    note("engine ready")
     p0 = ensemble(fit, W)
     sampler = EnsembleSampler(W, eng.ndim, eng, seed=1234, world_size=world, rank=rank,
                               group=(dist.group.WORLD if world > 1 else None), graph=not args.no_graph,
@@ -397,19 +409,23 @@ def run_gpu_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    note("sampler initialised, warm-up")
     for _ in range(args.warmup):
         sampler.step()
     extra_warm = 0
     while sampler.use_graph and not sampler.graph_active and sampler._graph_failed is None and extra_warm < 4:
         sampler.step()                       # the iteration is captured after its first eager steps
         extra_warm += 1
+    note(f"timed blocks (graph {sampler.graph_active}, p2p {sampler._px is not None})")
     with ClockSampler(local) as clk:
         blocks = time_blocks(sampler.step, args.steps, TIMED_BLOCKS, barrier, reduce_max)
     ms = sorted(blocks)[len(blocks) // 2]
     value = W * args.steps / (ms * 1e-3)
     acc = sampler.mean_acceptance()
     checksum = state_checksum(sampler)
+    note(f"{ms / args.steps:.3f} ms / step; profiling pass")
     stages = profile_pass(eng, sampler, args.steps)
+    note("end-to-end legs")
 
     # ---- end to end with host buffers
     shard = W // world
@@ -448,7 +464,26 @@ def run_gpu_arm(args):
         e2e_numpy = {"value": W * args.steps / (sorted(nb)[1] * 1e-3), "unit": UNIT,
                      "call": "fit.getLikelihood(vals[65536, 13]) with a pageable numpy array (staged through the engine's "
                              "pinned buffer), host array out"}
+        note("collapsed mode")
+        # optional `ll`-only mode (never the headline): the linear SZ chain as one operator, same engine
+        theta_dev = torch.from_numpy(host_theta).to(eng.device)
+        ll_staged = eng.loglike_device(theta_dev).clone()
+        eng.mode = "collapsed"
+        ll_coll = eng.loglike_device(theta_dev).clone()
+
+        def coll_step():
+            eng.loglike_device(theta_dev, out=ll_coll)
+
+        cb = time_blocks(coll_step, args.steps, 3, barrier, reduce_max)
+        eng.mode = "staged"
+        finc = torch.isfinite(ll_staged)
+        collapsed = {"value": W * args.steps / (sorted(cb)[1] * 1e-3), "unit": UNIT, "ms_per_call": sorted(cb)[1] / args.steps,
+                     "what": "jx_loglike_collapsed on the device-resident ensemble (K1 -> one DMMA GEMM with the operator "
+                             "built from the staged kernels -> K5); intermediate maps do not exist in this mode",
+                     "max_abs_dll_vs_staged": float((ll_staged[finc] - ll_coll[finc]).abs().max().item()),
+                     "inf_mask_equal": bool(torch.equal(finc, torch.isfinite(ll_coll)))}
     else:
+        collapsed = None
         # N > 1: the sampler iteration with the ensemble state in host memory between steps -- H2D of positions and
         # log-probs before, the two half-steps with their all-gathers, D2H of the new state after
         pin_c = torch.from_numpy(host_state.copy()).pin_memory()
@@ -474,6 +509,7 @@ def run_gpu_arm(args):
         e2e_numpy = None
         host_theta = host_state[rank * shard:(rank + 1) * shard].copy()
 
+    note("roofline / CPU baseline")
     line = None
     if rank == 0:
         pk = eng.packed
@@ -564,7 +600,7 @@ def run_gpu_arm(args):
                                          "p2p: accept kernel stores into every rank's buffer over NVLink, flags, no collective"
                                          if sampler._px is not None else "nccl all_gather_into_tensor per half-step"),
                             "p2p_fallback_reason": sampler._px_failed},
-                "clocks": clk.summary(), "e2e": e2e, "e2e_numpy": e2e_numpy,
+                "clocks": clk.summary(), "e2e": e2e, "e2e_numpy": e2e_numpy, "collapsed_mode": collapsed,
                 "gpu_launches": int(sampler.launches_per_step() * args.steps),
                 "gpu_launches_note": "kernels of libjoxsz_b200.so per timed block (K steps), replayed from one CUDA graph "
                                      "per iteration: 2 x (K1 K4 K2 K3 K7 K5 + propose accept scatter) + permutation",

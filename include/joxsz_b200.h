@@ -150,6 +150,12 @@ const char* jx_last_error(const jx_handle* h);
  * theta [W, ndim] -> ll [W]; -inf exactly where the reference returns -inf; never NaN. */
 int jx_loglike(jx_handle* h, const double* theta, int32_t W, double* ll, void* stream);
 
+/* Collapsed mode (optional, `ll` only): every step between the pressure profile and the consumed row of the filtered
+ * map is linear (joxsz_funcs.py:457-467), so row = L pp with a constant L [nh, nr].  L is built once per handle by
+ * pushing the nr unit profiles through the staged kernels above; the call is then K1 -> one GEMM -> tail.  Same
+ * inputs / outputs / -inf conventions as jx_loglike; the intermediate maps do not exist in this mode. */
+int jx_loglike_collapsed(jx_handle* h, const double* theta, int32_t W, double* ll, void* stream);
+
 /* ---- parity taps: every output pointer may be NULL (not produced).  Taps evaluate every walker,
  *      like the reference's component methods, regardless of prior flags. */
 

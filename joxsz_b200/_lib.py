@@ -55,6 +55,7 @@ PROTOTYPES = {
     "jx_destroy": (None, [_vp]),
     "jx_last_error": (C.c_char_p, [_vp]),
     "jx_loglike": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp]),
+    "jx_loglike_collapsed": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp]),
     "jx_profiles": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "jx_sz_project": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, _vp]),
     "jx_sz_maps": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, _vp, _vp]),

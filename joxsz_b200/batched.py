@@ -21,7 +21,7 @@ def _ptr(t):
 
 
 class BatchedLikelihood:
-    def __init__(self, fit=None, packed: PackedSetup | None = None, max_walkers=1024, device=None):
+    def __init__(self, fit=None, packed: PackedSetup | None = None, max_walkers=1024, device=None, mode=None):
         if not torch.cuda.is_available():
             raise _lib.JxError("BatchedLikelihood needs a CUDA device: the likelihood has no CPU implementation")
         self.lib = _lib.load()
@@ -43,6 +43,13 @@ class BatchedLikelihood:
         rc = self.lib.jx_create(C.byref(packed.struct()), C.byref(handle))
         _lib.check(rc, None)
         self._h = handle
+        #: "staged" (default): the reference-shaped pipeline, every intermediate map exists (K1 K2 K3 K7 K5);
+        #: "collapsed": the linear SZ chain folded into one constant operator, `ll` only (jx_loglike_collapsed).
+        #: JX_MODE in the environment sets the default.
+        import os
+        self.mode = mode or os.environ.get("JX_MODE", "staged")
+        if self.mode not in ("staged", "collapsed"):
+            raise ValueError("mode must be 'staged' or 'collapsed'")
         self._pinned_in = None
         self._pinned_out = None
         self._dev_in = None
@@ -100,8 +107,9 @@ class BatchedLikelihood:
             out = self._new(W)
         if W == 0:              # an empty tensor has a NULL data pointer, which the C ABI rejects
             return out
+        fn = self.lib.jx_loglike if self.mode == "staged" else self.lib.jx_loglike_collapsed
         with torch.cuda.device(self.device):
-            rc = self.lib.jx_loglike(self._h, _ptr(theta_dev), W, _ptr(out), self._stream())
+            rc = fn(self._h, _ptr(theta_dev), W, _ptr(out), self._stream())
         _lib.check(rc, self._h)
         return out
 

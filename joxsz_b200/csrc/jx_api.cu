@@ -175,6 +175,7 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     h->ev_ready = false;
     h->pending = false;
     h->side = nullptr;
+    h->collapsed_op = nullptr;
     memset(h->stage_ms, 0, sizeof h->stage_ms);
     memset(h->stage_launches, 0, sizeof h->stage_launches);
     jx_dev& d = h->d;
@@ -500,6 +501,78 @@ extern "C" int jx_loglike(jx_handle* h, const double* theta, int32_t W, double* 
         JX_CUDA(h, cudaEventRecord(h->ev[6], st));
         h->pending = true;
     }
+    return JX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// collapsed mode: the whole SZ chain between the pressure profile and the consumed row is linear (Abel projection,
+// spline fit, map synthesis, beam convolution, filter: joxsz_funcs.py:457-467), so row = L pp with one constant
+// operator L [nh, nr].  L is obtained by pushing the nr unit profiles through the STAGED kernels of this handle (same
+// arithmetic, no second implementation) the first time the mode is used; afterwards a likelihood call is
+// K1 -> one DMMA GEMM -> K5.  Offered for callers that only need `ll`; the staged path stays the reference-shaped one.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void collapse_unit_rows_kernel(double* pp, int n, int ld, int first) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * ld) return;
+    const int r = i / ld, c = i - r * ld;
+    pp[i] = (c == first + r) ? 1.0 : 0.0;
+}
+// lop[x, first + r] = sum_p rowp[p][r][x]
+__global__ void collapse_store_kernel(const double* rowp, int nparts, int W, int ld_row, int nh, double* lop, int ldl,
+                                      int first, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * nh) return;
+    const int r = i / nh, x = i - r * nh;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += rowp[((size_t)p * W + r) * ld_row + x];
+    lop[(size_t)x * ldl + first + r] = s;
+}
+}  // namespace
+
+static int build_collapsed(jx_handle* h, cudaStream_t st) {
+    jx_dev& d = h->d;
+    if (h->collapsed_op) return JX_OK;
+    double* lop = nullptr;
+    int rc = dev_alloc(h, &lop, (size_t)d.hp8 * d.nrp);
+    if (rc) return rc;
+    JX_CUDA(h, cudaMemsetAsync(lop, 0, sizeof(double) * (size_t)d.hp8 * d.nrp, st));
+    const int chunk = d.max_walkers < d.nr ? d.max_walkers : d.nr;
+    for (int first = 0; first < d.nr; first += chunk) {
+        const int n = d.nr - first < chunk ? d.nr - first : chunk;
+        collapse_unit_rows_kernel<<<(n * d.nrp + 255) / 256, 256, 0, st>>>(d.ws_pp, n, d.nrp, first);
+        JX_CUDA(h, cudaGetLastError());
+        JX_CUDA(h, jx_launch_project(d, d.ws_pp, n, d.proj_op, d.ncoef, d.ws_coef, st));
+        const double* row = nullptr;
+        int ld_row = 0, nparts = 1;
+        JX_CUDA(h, launch_map_filter(h, d.ws_coef, nullptr, n, nullptr, &row, &ld_row, &nparts, nullptr, st));
+        collapse_store_kernel<<<(n * d.nh + 255) / 256, 256, 0, st>>>(row, nparts, n, ld_row, d.nh, lop, d.nrp, first, n);
+        JX_CUDA(h, cudaGetLastError());
+    }
+    JX_CUDA(h, cudaStreamSynchronize(st));
+    h->collapsed_op = lop;
+    return JX_OK;
+}
+
+extern "C" int jx_loglike_collapsed(jx_handle* h, const double* theta, int32_t W, double* ll, void* stream) {
+    int rc = check_ready(h, theta, W);
+    if (rc) return rc;
+    if (!ll) return fail(h, JX_ERR_INVALID, "ll is NULL");
+    if (W == 0) return JX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    jx_dev& d = h->d;
+    if ((rc = build_collapsed(h, st))) return rc;
+    JX_CUDA(h, jx_launch_profiles(d, theta, W, d.ws_pp, d.nrp, d.ws_tsz, d.ws_ne, d.ws_tx, d.ws_flags, d.ws_prior,
+                                  d.ws_integ, st));
+    JX_CUDA(h, cudaEventRecord(h->ev_fork, st));
+    JX_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    JX_CUDA(h, jx_launch_xray(d, theta, d.ws_ne, d.ws_tx, W, nullptr, d.ws_xlike, d.ws_flags, h->side));
+    JX_CUDA(h, cudaEventRecord(h->ev_join, h->side));
+    // row [W, hpf] = pp [W, nrp] . L^T: the partial-row buffer of the staged path is free in this mode
+    JX_CUDA(h, jx_launch_gemm_nt(d.ws_pp, d.nrp, h->collapsed_op, d.nrp, d.ws_rowp, d.hpf, W, d.hp8, d.nrp, st));
+    JX_CUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
+    JX_CUDA(h, jx_launch_tail(d, theta, d.ws_rowp, d.hpf, 1, d.ws_tsz, d.ws_flags, d.ws_prior, d.ws_xlike, d.ws_integ, W,
+                              nullptr, nullptr, nullptr, ll, nullptr, st));
     return JX_OK;
 }
 

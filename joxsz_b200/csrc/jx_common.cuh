@@ -121,6 +121,7 @@ struct jx_handle {
     cudaStream_t side;
     cudaEvent_t ev_fork, ev_join;
     int pending_launches[JX_NSTAGE];
+    double* collapsed_op;    // [hp8, nrp]: row = collapsed_op . pp (collapsed mode, built on first use)
 };
 
 // ---- launchers implemented by the kernel files (all asynchronous on `st`)

@@ -237,3 +237,21 @@ def test_pinned_host_input(engine, golden):
     out = engine(pinned)
     assert isinstance(out, torch.Tensor) and not out.is_cuda
     assert np.array_equal(out.numpy(), ref)
+
+
+@pytest.mark.gpu
+def test_collapsed_mode_matches_staged_and_golden(cl1226_fit, golden):
+    """Optional `ll`-only mode: the linear SZ chain folded into one operator built from the staged kernels themselves
+    (jx_loglike_collapsed).  Same -inf mask, log-likelihoods within 1e-8 of the staged path and 1e-6 of the
+    reference-recorded goldens."""
+    from joxsz_b200.batched import BatchedLikelihood
+    thetas = golden["thetas"]
+    staged = BatchedLikelihood(cl1226_fit, max_walkers=256)
+    coll = BatchedLikelihood(cl1226_fit, max_walkers=100, mode="collapsed")      # < nr walkers: operator built in chunks
+    a, b = staged(thetas), coll(thetas)
+    fin = np.isfinite(golden["ll"])
+    assert np.array_equal(np.isfinite(a), fin) and np.array_equal(np.isfinite(b), fin)
+    assert np.max(np.abs(a[fin] - b[fin])) < 1e-8
+    assert np.max(np.abs(b[fin] - golden["ll"][fin])) < 1e-6
+    assert not np.isnan(b).any()
+    staged.close(); coll.close()
