@@ -157,36 +157,51 @@ class ClockSampler:
 # CPU legs (oracle port of the reference's per-walker path)
 # ----------------------------------------------------------------------------------------------
 
-_ORACLE_SETUP = None
+_ORACLE_SETUPS = {}
 
 
-def _cpu_init(workload="cl1226"):
-    global _ORACLE_SETUP, WORKLOAD
-    WORKLOAD = workload
+def _oracle_setup(workload):
+    s = _ORACLE_SETUPS.get(workload)
+    if s is None:
+        from helpers import oracle_setup_from_fit
+        s = _ORACLE_SETUPS[workload] = oracle_setup_from_fit(build_cluster(workload))
+    return s
+
+
+def _cpu_init():
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-    from helpers import oracle_setup_from_fit
-    _ORACLE_SETUP = oracle_setup_from_fit(build_cluster(workload))
 
 
-def _cpu_eval(theta):
+def _cpu_prepare(workload):
+    _oracle_setup(workload)
+    time.sleep(0.25)          # long enough that every worker of the pool takes exactly one of these tasks
+    return os.getpid()
+
+
+def _cpu_eval(task):
     from oracle import joxsz_oracle as orc
-    return orc.get_likelihood(theta, _ORACLE_SETUP)
+    workload, theta = task
+    return orc.get_likelihood(theta, _oracle_setup(workload))
 
 
-def cpu_reference_rate(thetas, pool):
+def cpu_reference_rate(thetas, pool, workload=None):
     """evals/s of the literal per-walker path, one task per walker like emcee's pool.map (joxsz_main.py:203-208)."""
+    workload = workload or WORKLOAD
+    pool.map(_cpu_prepare, [workload] * pool._processes, chunksize=1)     # set-ups built before the clock starts
     t0 = time.perf_counter()
-    out = pool.map(_cpu_eval, list(thetas), chunksize=1)
+    out = pool.map(_cpu_eval, [(workload, th) for th in thetas], chunksize=1)
     dt = time.perf_counter() - t0
     return len(thetas) / dt, dt, np.array(out)
 
 
-def make_pool(workload=None):
+def make_pool():
+    """Process pool over all host cores.  Created BEFORE the process touches CUDA / NCCL: forking a multi-threaded
+    parent later can leave a child stuck on a lock that some other thread held at fork time."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     ctx = mp.get_context("fork")
-    pool = ctx.Pool(cores, initializer=_cpu_init, initargs=(workload or WORKLOAD,))
+    pool = ctx.Pool(cores, initializer=_cpu_init)
     pool.map(_noop, range(cores * 2))
     return pool, cores
 
@@ -199,8 +214,8 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    fit = build_cluster()
     pool, cores = make_pool()
+    fit = build_cluster()
     per_step = max(cores * 16, 128)
     thetas = ensemble(fit, per_step * (args.steps + args.warmup))
     for w in range(args.warmup):
@@ -310,7 +325,7 @@ def profile_pass(eng, sampler, steps):
     return st
 
 
-def run_secondary(name, world, rank, local, dist, args, barrier, reduce_max):
+def run_secondary(name, world, rank, local, dist, args, barrier, reduce_max, pool, cores):
     """BASELINE configs 3 / 5: 8,192 walkers per rank of a larger synthetic cluster, a few iterations."""
     import torch
     from joxsz_b200.batched import BatchedLikelihood
@@ -345,9 +360,7 @@ def run_secondary(name, world, rank, local, dist, args, barrier, reduce_max):
         k3_s = stage_ms["szmap"] * 1e-3
         # parity of the device path against the literal per-walker oracle on a small sample of the final ensemble
         theta = sampler.coords_host()[:args.secondary_cpu_sample]
-        pool, cores = make_pool(name)
-        cpu_rate, cpu_dt, cpu_ll = cpu_reference_rate(theta, pool)
-        pool.close()
+        cpu_rate, cpu_dt, cpu_ll = cpu_reference_rate(theta, pool, name)
         gpu_ll = eng(theta)
         fin = np.isfinite(cpu_ll)
         out = {"config": workload_config(Wn, world, name), "value": Wn * steps / (ms * 1e-3), "unit": UNIT,
@@ -379,6 +392,7 @@ def run_gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    pool, cores = make_pool() if rank == 0 else (None, 0)      # before CUDA is initialised (see make_pool)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -581,10 +595,8 @@ def run_gpu_arm(args):
                                             "achieved_gbs": both_gbs,
                                             "frac_of_measured_hbm": both_gbs / hbm_peak if both_gbs else None}}
         # bounded CPU baseline on this box's cores + parity of the device path on the same walkers
-        pool, cores = make_pool()
         sample_n = max(cores * 64, 512)
         cpu_rate, cpu_dt, cpu_ll = cpu_reference_rate(host_theta[:sample_n], pool)
-        pool.close()
         gpu_ll = eng(host_theta[:sample_n])
         fin = np.isfinite(cpu_ll)
         parity = float(np.max(np.abs(gpu_ll[fin] - cpu_ll[fin]))) if fin.any() else None
@@ -617,7 +629,7 @@ def run_gpu_arm(args):
         sec = {}
         for name in ("synth255", "synth511"):
             try:
-                r = run_secondary(name, world, rank, local, dist, args, barrier, reduce_max)
+                r = run_secondary(name, world, rank, local, dist, args, barrier, reduce_max, pool, cores)
             except Exception as e:          # the headline line must still be printed
                 r = {"error": f"{type(e).__name__}: {e}"}
             if rank == 0:
@@ -625,6 +637,7 @@ def run_gpu_arm(args):
         if rank == 0:
             line["secondary"] = sec
     if rank == 0:
+        pool.close()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -40,6 +40,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    pool, cores = bench.make_pool() if rank == 0 else (None, 0)      # forked before CUDA is initialised
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -93,8 +94,7 @@ def main():
         peaks, useds = [peak], [used]
     if rank == 0:
         theta = mcmc.coords_host()[:args.cpu_sample]
-        pool, cores = bench.make_pool(args.workload)
-        cpu_rate, cpu_dt, cpu_ll = bench.cpu_reference_rate(theta, pool)
+        cpu_rate, cpu_dt, cpu_ll = bench.cpu_reference_rate(theta, pool, args.workload)
         pool.close()
         gpu_ll = eng(theta)
         lp_state = mcmc.log_prob_host()[:args.cpu_sample]
