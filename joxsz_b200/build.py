@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjoxsz_b200.so")
-SOURCES = ["jx_api.cu", "k1_profiles.cu", "k2_project.cu", "k3_szmap.cu", "k3w_szmap.cu", "k3l_szmap.cu", "k4_xray.cu", "k5_tail.cu", "k6_stretch.cu", "k7_filter.cu"]
+SOURCES = ["jx_api.cu", "k1_profiles.cu", "k2_project.cu", "k3_szmap.cu", "k3w_szmap.cu", "k3l_szmap.cu", "k3l2_szmap.cu", "k4_xray.cu", "k5_tail.cu", "k6_stretch.cu", "k7_filter.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

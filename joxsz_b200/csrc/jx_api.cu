@@ -413,9 +413,12 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
         } else {
             cudaError_t e = jx_szmap_large_configure(d);
             if (e == cudaSuccess) e = jx_filter_configure(d);
+            d.k3l2 = jx_szmap_large2_ok(d) ? 1 : 0;
+            if (e == cudaSuccess && d.k3l2) e = jx_szmap_large2_configure(d);
             if (e != cudaSuccess) rc = cuda_fail(h, e, "configure large-map kernel");
-            if (!rc) rc = dev_alloc(h, &d.ws_scratch, (size_t)h->sm_count * d.hp8 * d.xs_pitch);
-            if (!rc && d.bmix) rc = dev_alloc(h, &d.ws_scratch2, (size_t)h->sm_count * d.hp8 * d.xs_pitch);
+            const size_t nscr = (size_t)(d.k3l2 ? 2 : 1) * h->sm_count;       // one scratch map pair per resident CTA
+            if (!rc) rc = dev_alloc(h, &d.ws_scratch, nscr * d.hp8 * d.xs_pitch);
+            if (!rc && d.bmix) rc = dev_alloc(h, &d.ws_scratch2, nscr * d.hp8 * d.xs_pitch);
         }
     }
     if (!rc) {
@@ -448,7 +451,8 @@ static cudaError_t launch_map_filter(jx_handle* h, const double* coef, const uin
         *row = d.ws_rowp; *ld_row = d.hpf; *nparts = jx_filter_parts(d);
         return jx_launch_filter(d, d.ws_tri, W, d.ws_rowp, st);
     }
-    e = jx_launch_szmap_large(d, coef, flags, W, h->sm_count, convq, d.ws_tri, d.ws_scratch, d.ws_scratch2, st);
+    e = d.k3l2 ? jx_launch_szmap_large2(d, coef, flags, W, h->sm_count, convq, d.ws_tri, d.ws_scratch, d.ws_scratch2, st)
+               : jx_launch_szmap_large(d, coef, flags, W, h->sm_count, convq, d.ws_tri, d.ws_scratch, d.ws_scratch2, st);
     if (e == cudaSuccess && ev_mid) e = cudaEventRecord(ev_mid, st);
     if (e != cudaSuccess) return e;
     *row = d.ws_rowp; *ld_row = d.hpf; *nparts = jx_filter_parts(d);

@@ -50,6 +50,7 @@ struct jx_dev {
     int nbeam;               // beam half-side incl. the centre
     int k3_direct;           // map kernel convolves along y directly (jx_szmap_direct_ok at jx_create)
     int k3_ws;               // two walkers in flight per SM: the warp-specialised map kernel (k3w_szmap.cu)
+    int k3l2;                // large maps: the two-CTA-per-SM form of the L2-staged kernel (k3l2_szmap.cu)
     const double* bmix;      // [28, bmix_pitch] beam in (y offset, kx), zero rows beyond nbeam; NULL when nbeam > 28
     int bmix_pitch;          // JX_BMIX_PITCH for the cyclic length 256, nq rounded up to 4 otherwise
     const double* cmat_t;    // [nh, nh] transposed on upload: [kx, v]
@@ -172,6 +173,13 @@ size_t jx_szmap_large_smem_bytes(const jx_dev& d);
 cudaError_t jx_szmap_large_configure(const jx_dev& d);
 cudaError_t jx_launch_szmap_large(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
                                   double* convq, double* tri, double* scratch, double* scratch2, cudaStream_t st);
+
+// two CTAs per SM, transforms straight from / to the L2 scratch maps (k3l2_szmap.cu)
+bool jx_szmap_large2_ok(const jx_dev& d);
+size_t jx_szmap_large2_smem_bytes(const jx_dev& d);
+cudaError_t jx_szmap_large2_configure(const jx_dev& d);
+cudaError_t jx_launch_szmap_large2(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
+                                   double* convq, double* tri, double* scratch, double* scratch2, cudaStream_t st);
 
 // ---- small device helpers
 JX_D double warp_sum(double v) {

@@ -1,0 +1,312 @@
+// K3L2 -- the large-map stage (cyclic length 512 / 1024, direct y convolution) re-laid-out for occupancy.
+//
+// Same mathematics and phases as k3l_szmap.cu (reference joxsz_funcs.py:462-464) -- results identical at P = 512 and
+// equal within rounding at P = 1024 (a quarter of the spectrum samples is taken from its mirror image) -- with a
+// different resource plan.  ncu on k3l_szmap_kernel<2> (profiles/
+// r02a_k3l255_ncu_summary.txt): 8 warps per SM at 255 registers, FP64 pipe 33 % busy, 0.46 eligible warps per
+// cycle -- the kernel waits on its own dependency chains because the staging lines of the row transforms (two lines
+// of P/2+1 complex samples per 16-thread group) fill the shared memory of an SM with one 256-thread CTA.  Here
+//   * a row transform reads its samples straight from the L2-resident scratch map and writes its spectrum straight to
+//     the other scratch map (out of place: A1 xs -> xc, B xc -> xs, C xs -> packed triangle), so a group only needs
+//     its 4 KB exchange tile: two CTAs of 256 threads per SM, 128 registers each (16 warps per SM);
+//   * the y convolution takes 16 rows per thread (16 accumulators + 28 taps in 128 registers);
+//   * at P = 1024 the s = 3 branch of the radix-4 decimation is never computed: its spectrum samples are the mirror
+//     images X[P - K] of the s = 1 branch (every sequence of the stage is even), which stores both (-25 % of the
+//     transform work);
+//   * the spline coefficients of the next walker arrive by TMA bulk copy while the current walker's transforms and
+//     convolution run (they are only read by the synthesis).
+#include "k3_common.cuh"
+
+namespace {
+
+constexpr int K3M_NT = 256;                         // threads per CTA (16 transform groups), two CTAs per SM
+constexpr int K3M_NB = JX_BMIX_ROWS, K3M_UB = 16, K3M_PF = 4;
+
+struct k3m_layout {
+    size_t tw, twp, xbuf, coef, mbar, total;
+};
+
+__host__ __device__ inline k3m_layout k3m_make_layout(const jx_dev& d) {
+    k3m_layout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~size_t(15); return at; };
+    L.tw = take(256 * sizeof(double2));
+    L.twp = take((size_t)d.npad * sizeof(double2));
+    L.xbuf = take((size_t)(K3M_NT / 16) * JX_XB_ELEMS * sizeof(double2));
+    L.coef = take((size_t)d.ncoef * sizeof(double));
+    L.mbar = take(sizeof(uint64_t));
+    L.total = o;
+    return L;
+}
+
+template <int R>
+JX_D void mul_wr2(double& r, double& i, int e) {
+    if constexpr (R == 2) {
+        if (e & 1) { r = -r; i = -i; }
+    } else {
+        e &= 3;
+        if (e == 1) { double t = r; r = i; i = -t; }          // * (-i)
+        else if (e == 2) { r = -r; i = -i; }
+        else if (e == 3) { double t = r; r = -i; i = t; }      // * (+i)
+    }
+}
+
+// Forward DFT of the even sequence x[n] = ld(fold(n)), n < P = 256 R, by one 16-thread group: st(K, re, im) receives
+// X[K] for every K <= P/2 exactly once.  Radix-R decimation in frequency around the register FFT-256:
+//   y_s[m] = w_P^(s m) sum_j x[m + 256 j] w_R^(s j),   X[R k + s] = FFT256(y_s)[k];
+// for R = 4 the branch s = 3 is skipped: X[4 k + 3] = X[P - 4 k - 3] = X[4 (255 - k) + 1] comes out of branch s = 1.
+template <int R, class LD, class ST>
+JX_D void k3m_group_fft_even(int t, unsigned gmask, LD&& ld, ST&& st, const double2* __restrict__ tw256,
+                             const double2* __restrict__ twp, double2* __restrict__ xbuf) {
+    constexpr int P = 256 * R, NS = R == 4 ? 3 : R;
+    double re[16], im[16];
+#pragma unroll 1
+    for (int s = 0; s < NS; ++s) {
+        // the gather runs in chunks of G samples: all loads of a chunk are in flight together (L2 latency), and the
+        // compiler barrier between chunks keeps it from hoisting every load of the line (the kernel lives in 128
+        // registers: two CTAs per SM)
+        constexpr int G = 8 / R;
+#pragma unroll
+        for (int j0 = 0; j0 < 16; j0 += G) {
+            double2 v[G][R];
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int n = t + 16 * (j0 + g) + 256 * j;
+                    v[g][j] = ld(n <= P / 2 ? n : P - n);
+                }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int m = t + 16 * (j0 + g);
+                double ar = 0.0, ai = 0.0;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    double vr = v[g][j].x, vi = v[g][j].y;
+                    mul_wr2<R>(vr, vi, s * j);
+                    ar += vr; ai += vi;
+                }
+                if (s) {
+                    const double2 w = twp[(s * m) & (P - 1)];
+                    const double tr = ar * w.x - ai * w.y;
+                    ai = ar * w.y + ai * w.x;
+                    ar = tr;
+                }
+                re[j0 + g] = ar; im[j0 + g] = ai;
+            }
+            asm volatile("" ::: "memory");
+        }
+        fft256_pass1(t, re, im, tw256, xbuf);
+        __syncwarp(gmask);
+        fft256_pass2(t, re, im, xbuf);
+        __syncwarp(gmask);
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            const int K = R * (t + 16 * rev16(p)) + s;
+            if (K <= P / 2) st(K, re[p], im[p]);
+            else if (R == 4 && s == 1) st(P - K, re[p], im[p]);        // the s = 3 samples, by evenness
+        }
+    }
+}
+
+// y convolution of UB consecutive rows of column kx (same scheme and summation order as k3l_szmap.cu / k3_szmap.cu)
+JX_D void k3m_yconv(const double* __restrict__ in, int pitch, int kx, int u0, int H, const double (&tap)[K3M_NB],
+                    double (&acc)[K3M_UB]) {
+    constexpr int NIN = K3M_UB + 2 * (K3M_NB - 1);
+    auto fetch = [&](int ii) {
+        const int up = u0 - (K3M_NB - 1) + ii, ua = up < 0 ? -up : up;
+        return ua < H ? __ldcg(in + (size_t)ua * pitch + kx) : 0.0;
+    };
+#pragma unroll
+    for (int k = 0; k < K3M_UB; ++k) acc[k] = 0.0;
+    double xq[K3M_PF];
+#pragma unroll
+    for (int q = 0; q < K3M_PF; ++q) xq[q] = fetch(q);
+#pragma unroll
+    for (int ii = 0; ii < NIN; ++ii) {
+        const double x = xq[ii % K3M_PF];
+        if (ii + K3M_PF < NIN) xq[ii % K3M_PF] = fetch(ii + K3M_PF);
+#pragma unroll
+        for (int k = 0; k < K3M_UB; ++k) {
+            const int j = ii - (K3M_NB - 1) - k < 0 ? k + (K3M_NB - 1) - ii : ii - (K3M_NB - 1) - k;
+            if (j < K3M_NB) acc[k] = fma(tap[j], x, acc[k]);
+        }
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(K3M_NT, 2) k3l2_szmap_kernel(const __grid_constant__ k3_args a) {
+    extern __shared__ __align__(128) unsigned char k3m_raw[];
+    constexpr int P = 256 * R, Q = P / 2 + 1, NT = K3M_NT;
+    const jx_dev& d = a.d;
+    const int H = d.nh, hp8 = d.hp8;
+    const k3m_layout L = k3m_make_layout(d);
+    double2* tw_s = reinterpret_cast<double2*>(k3m_raw + L.tw);
+    double2* twp_s = reinterpret_cast<double2*>(k3m_raw + L.twp);
+    double2* xbuf_all = reinterpret_cast<double2*>(k3m_raw + L.xbuf);
+    double* coef_s = reinterpret_cast<double*>(k3m_raw + L.coef);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(k3m_raw + L.mbar);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = tid >> 4, t = tid & 15, ngroups = NT >> 4;
+    const unsigned gmask = 0xffffu << (lane & 16);
+    double2* xbuf = xbuf_all + (size_t)grp * JX_XB_ELEMS;
+    const uint32_t coef_bytes = (uint32_t)(d.ncoef * sizeof(double));
+    const int pitch = d.xs_pitch;
+    double* xs = a.scratch + (size_t)blockIdx.x * hp8 * pitch;      // synthesised map, then the convolved spectra
+    double* xc = a.scratch2 + (size_t)blockIdx.x * hp8 * pitch;     // row spectra
+
+    for (int i = tid; i < 256; i += NT) fft256_make_twiddle(i, tw_s[i]);
+    for (int i = tid; i < P; i += NT) {
+        const double ang = -2.0 * 3.14159265358979323846 * (double)i / (double)P;
+        twp_s[i] = make_double2(cos(ang), sin(ang));
+    }
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const int w_first = blockIdx.x;
+    if (tid == 0 && w_first < a.W) {
+        mbar_expect_tx(mbar, coef_bytes);
+        tma_bulk_g2s(coef_s, a.coef + (size_t)w_first * d.ncoef, coef_bytes, mbar);
+    }
+
+    const int npair = (H + 1) >> 1;
+    int it = 0;
+    for (int w = w_first; w < a.W; w += gridDim.x, ++it) {
+        // only the bits the profile kernel wrote decide the skip (see k3_szmap.cu)
+        const bool skip = a.flags && (a.flags[w] & ~(uint32_t)JX_FLAG_XNONPOS) != 0u;
+        mbar_wait(mbar, (uint32_t)(it & 1));
+        if (!skip) {
+            // ---- A0: synthesise the quarter-plane map (u <= v listed, mirrored on store)
+            const int4* tab = reinterpret_cast<const int4*>(d.synth);
+            for (int base = 0; base < d.nsynth; base += 8 * NT) {
+                int4 e[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = base + k * NT + tid;
+                    e[k] = i < d.nsynth ? __ldg(tab + i) : make_int4(0, 0, 0xffff0000, 0);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int sg = e[k].z & 0xffff, u = (e[k].z >> 16) & 0xffff, v = e[k].w & 0xffff;
+                    if (u != 0xffff) {
+                        const double z = spline_eval(coef_s, d.nseg, sg, __hiloint2double(e[k].y, e[k].x));
+                        __stcg(xs + (size_t)u * pitch + v, z);
+                        __stcg(xs + (size_t)v * pitch + u, z);
+                    }
+                }
+            }
+        }
+        __syncthreads();                       // the coefficients have been read (or are not needed): refill them
+        {
+            const int wn = w + gridDim.x;
+            if (tid == 0 && wn < a.W) {
+                mbar_expect_tx(mbar, coef_bytes);
+                tma_bulk_g2s(coef_s, a.coef + (size_t)wn * d.ncoef, coef_bytes, mbar);
+            }
+        }
+        if (skip) continue;
+
+        // ---- A1: rows along x, xs -> xc
+        for (int rp = grp; rp < npair; rp += ngroups) {
+            const int u0 = 2 * rp, u1 = u0 + 1;
+            const bool has1 = u1 < H;
+            const double* r0 = xs + (size_t)u0 * pitch;
+            const double* r1 = xs + (size_t)(has1 ? u1 : u0) * pitch;
+            double* o0 = xc + (size_t)u0 * pitch;
+            double* o1 = xc + (size_t)u1 * pitch;
+            k3m_group_fft_even<R>(
+                t, gmask,
+                [&](int f) { return f < H ? make_double2(__ldcg(r0 + f), has1 ? __ldcg(r1 + f) : 0.0) : make_double2(0.0, 0.0); },
+                [&](int K, double vr, double vi) { __stcg(o0 + K, vr); if (has1) __stcg(o1 + K, vi); },
+                tw_s, twp_s, xbuf);
+        }
+        __syncthreads();
+
+        // ---- B: 55-tap convolution along y, xc -> xs; lane = column, tasks of 16 rows x 32 columns
+        {
+            const int ncw = (Q + 31) >> 5, nrb = (H + K3M_UB - 1) / K3M_UB, ntask = ncw * nrb, nw = NT >> 5;
+            const int t_lo = (int)(((long)warp * ntask) / nw), t_hi = (int)(((long)(warp + 1) * ntask) / nw);
+            double tap[K3M_NB];
+            int cw_have = -1;
+            for (int task = t_lo; task < t_hi; ++task) {
+                const int cw = task / nrb, u0 = (task % nrb) * K3M_UB;
+                const int kx = 32 * cw + lane;
+                const bool on = kx < Q;
+                const int kxc = on ? kx : Q - 1;
+                if (cw != cw_have) {
+#pragma unroll
+                    for (int j = 0; j < K3M_NB; ++j) tap[j] = __ldg(d.bmix + (size_t)j * d.bmix_pitch + kxc);
+                    cw_have = cw;
+                }
+                double acc[K3M_UB];
+                k3m_yconv(xc, pitch, kxc, u0, H, tap, acc);
+#pragma unroll
+                for (int k = 0; k < K3M_UB; ++k)
+                    if (on && u0 + k < H) __stcg(xs + (size_t)(u0 + k) * pitch + kx, acc[k]);
+            }
+        }
+        __syncthreads();
+
+        // ---- C: rows back to pixel space, xs -> packed triangle (and the quarter-plane tap)
+        double* cq = a.convq ? a.convq + (size_t)w * H * H : nullptr;
+        for (int rp = grp; rp < npair; rp += ngroups) {
+            const int u0 = 2 * rp, u1 = u0 + 1;
+            const bool has1 = u1 < H;
+            const double* r0 = xs + (size_t)u0 * pitch;
+            const double* r1 = xs + (size_t)(has1 ? u1 : u0) * pitch;
+            double* tri0 = a.tri + (size_t)w * d.ktri + (u0 * H - ((u0 * (u0 - 1)) >> 1) - u0);   // + v
+            double* tri1 = tri0 + (H - u0 - 1);
+            k3m_group_fft_even<R>(
+                t, gmask,
+                [&](int f) { return make_double2(__ldcg(r0 + f), has1 ? __ldcg(r1 + f) : 0.0); },
+                [&](int v, double vr, double vi) {
+                    if (v < H) {
+                        if (v >= u0) tri0[v] = vr;
+                        if (has1 && v >= u1) tri1[v] = vi;
+                        if (cq) {
+                            cq[(size_t)u0 * H + v] = vr;
+                            if (has1) cq[(size_t)u1 * H + v] = vi;
+                        }
+                    }
+                },
+                tw_s, twp_s, xbuf);
+        }
+        __syncthreads();        // every read of xs is done before the next walker's synthesis overwrites it
+    }
+}
+
+}  // namespace
+
+bool jx_szmap_large2_ok(const jx_dev& d) {
+    if (const char* e = getenv("JX_K3L2")) if (!atoi(e)) return false;
+    return (d.npad == 512 || d.npad == 1024) && d.bmix && d.nbeam <= K3M_NB && k3m_make_layout(d).total <= 115712;
+}
+
+size_t jx_szmap_large2_smem_bytes(const jx_dev& d) { return k3m_make_layout(d).total; }
+
+cudaError_t jx_szmap_large2_configure(const jx_dev& d) {
+    const int smem = (int)k3m_make_layout(d).total;
+    cudaError_t e = d.npad == 512
+        ? cudaFuncSetAttribute(k3l2_szmap_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+        : cudaFuncSetAttribute(k3l2_szmap_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return e;
+}
+
+// scratch / scratch2: [min(W, 2 sm_count)][hp8][xs_pitch] doubles each
+cudaError_t jx_launch_szmap_large2(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
+                                   double* convq, double* tri, double* scratch, double* scratch2, cudaStream_t st) {
+    if (W <= 0) return cudaSuccess;
+    k3_args a;
+    a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.tri = tri; a.scratch = scratch; a.scratch2 = scratch2;
+    const size_t smem = k3m_make_layout(d).total;
+    const int grid = W < 2 * sm_count ? W : 2 * sm_count;
+    if (d.npad == 512)
+        k3l2_szmap_kernel<2><<<grid, K3M_NT, smem, st>>>(a);
+    else
+        k3l2_szmap_kernel<4><<<grid, K3M_NT, smem, st>>>(a);
+    return cudaGetLastError();
+}
