@@ -540,16 +540,30 @@ def run_gpu_arm(args):
         peak_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         fp = measured_fp64_peaks(local)
         k3_s = (k3_ms / max(k3_n, 1)) * 1e-3
-        lane = fp64_lane_ops(pk)
+        lane_model = fp64_lane_ops(pk)
+        lane, lane_src, tr = lane_model, "counted from the kernel's structure (bench.fp64_lane_ops)", None
+        map_kernel = "k3_szmap_kernel" if pk.map_ops.P == 256 else "k3l_szmap_kernel"
+        try:
+            if WORKLOAD == "cl1226":
+                tr = json.load(open(os.path.join(ROOT, "profiles", "k3_ncu_traffic.json")))
+                map_kernel = tr.get("kernel", map_kernel)
+                if "fp64_lane_ops_per_walker" in tr:           # the executed count, from ncu's FP64-pipe instruction counter
+                    lane, lane_src = tr["fp64_lane_ops_per_walker"], "ncu: " + tr.get("fp64_lane_ops_how", "")
+        except Exception:
+            tr = None
         lane_rate = lane * nw / k3_s if k3_n else None
         lane_peak = fp["dfma_tflops"] * 1e12 / 2.0            # one DFMA = 2 flop = one lane-operation
         hbm_gbs = alg["szmap"] * nw / k3_s / 1e9 if k3_n else None
-        map_kernel = "k3_szmap_kernel" if pk.map_ops.P == 256 else "k3l_szmap_kernel"
         roof = {"bound": "fp64", "kernel": map_kernel,
                 "achieved": 2.0 * lane_rate / 1e12 if lane_rate else None, "peak": fp["dfma_tflops"], "unit": "TFLOP/s",
                 "frac": lane_rate / lane_peak if lane_rate and lane_peak else None, "traffic": None,
                 "peak_source": "DFMA microbenchmark in this run (scripts/jx_peaks.cu); MEASURED_PEAKS.json has no FP64 figure",
-                "executed_fp64_lane_ops_per_walker": lane, "walkers_per_launch": nw,
+                "executed_fp64_lane_ops_per_walker": lane, "lane_ops_source": lane_src,
+                "lane_ops_per_walker_structural_count": lane_model, "walkers_per_launch": nw,
+                "practical_ceiling": "a DFMA stream with two fresh 64-bit sources per instruction (the y convolution's "
+                                     "pattern) issues at 0.38-0.41 of a warp-instruction / clock / scheduler on B200 against "
+                                     "0.487 for the peak pattern a=fma(a,m,c): scripts/dfma_pattern_microbench.cu, "
+                                     "profiles/r02_results.md",
                 "avg_launch_ms": k3_s * 1e3, "launches_timed": int(k3_n),
                 "timing": "CUDA events around every kernel in an eager pass of `steps` iterations right after the timed "
                           "blocks (the timed blocks replay one CUDA graph per iteration, which has no per-kernel events)",
@@ -559,16 +573,11 @@ def run_gpu_arm(args):
                 "hbm_form": {"alg_bytes_per_walker": alg["szmap"], "achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak,
                              "frac": hbm_gbs / hbm_peak if hbm_gbs else None, "peak_source": peak_src},
                 "alg_flops_per_walker_survey_8d": flops["szmap"]}
-        try:
-            if WORKLOAD != "cl1226":
-                raise KeyError("no ncu capture for this workload")
-            tr = json.load(open(os.path.join(ROOT, "profiles", "k3_ncu_traffic.json")))
+        if tr is not None:
             roof["traffic"] = tr["dram_bytes_per_launch"] * (nw / tr["walkers_per_launch"])
             roof["traffic_source"] = tr.get("source")
             roof["ncu"] = {k: tr[k] for k in ("fp64_pipe_busy_frac", "shared_pipe_busy_frac", "issue_slots_busy_frac",
-                                              "fp64_lane_ops_per_walker") if k in tr}
-        except Exception:
-            pass
+                                              "fp64_lane_ops_per_walker", "gpu_time_ms_under_ncu") if k in tr}
         ncalls = max(k3_n, 1)
         stage_ms = {k: (v[0] / ncalls) for k, v in stages.items()}
 

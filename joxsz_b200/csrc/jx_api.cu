@@ -416,7 +416,7 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
             d.k3l2 = jx_szmap_large2_ok(d) ? 1 : 0;
             if (e == cudaSuccess && d.k3l2) e = jx_szmap_large2_configure(d);
             if (e != cudaSuccess) rc = cuda_fail(h, e, "configure large-map kernel");
-            const size_t nscr = (size_t)(d.k3l2 ? 2 : 1) * h->sm_count;       // one scratch map pair per resident CTA
+            const size_t nscr = (size_t)h->sm_count;                           // one scratch map pair per resident CTA
             if (!rc) rc = dev_alloc(h, &d.ws_scratch, nscr * d.hp8 * d.xs_pitch);
             if (!rc && d.bmix) rc = dev_alloc(h, &d.ws_scratch2, nscr * d.hp8 * d.xs_pitch);
         }

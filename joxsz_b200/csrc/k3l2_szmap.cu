@@ -8,7 +8,9 @@
 // of P/2+1 complex samples per 16-thread group) fill the shared memory of an SM with one 256-thread CTA.  Here
 //   * a row transform reads its samples straight from the L2-resident scratch map and writes its spectrum straight to
 //     the other scratch map (out of place: A1 xs -> xc, B xc -> xs, C xs -> packed triangle), so a group only needs
-//     its 4 KB exchange tile: two CTAs of 256 threads per SM, 128 registers each (16 warps per SM);
+//     its 4 KB exchange tile: one CTA of 512 threads per SM at 128 registers (16 warps per SM instead of 8, and still
+//     one scratch-map pair per SM: two CTAs per SM would double the working set and push it out of the 126 MB L2 --
+//     measured: L2 hit rate 79 % -> 69 %, 6 GB of DRAM traffic per launch, slower);
 //   * the y convolution takes 16 rows per thread (16 accumulators + 28 taps in 128 registers);
 //   * at P = 1024 the s = 3 branch of the radix-4 decimation is never computed: its spectrum samples are the mirror
 //     images X[P - K] of the s = 1 branch (every sequence of the stage is even), which stores both (-25 % of the
@@ -19,8 +21,8 @@
 
 namespace {
 
-constexpr int K3M_NT = 256;                         // threads per CTA (16 transform groups), two CTAs per SM
-constexpr int K3M_NB = JX_BMIX_ROWS, K3M_UB = 16, K3M_PF = 4;
+constexpr int K3M_NT = 512;                         // threads per CTA: 32 transform groups, 16 warps, one CTA per SM
+constexpr int K3M_NB = JX_BMIX_ROWS, K3M_UB = 16, K3M_PF = 8;
 
 struct k3m_layout {
     size_t tw, twp, xbuf, coef, mbar, total;
@@ -135,7 +137,7 @@ JX_D void k3m_yconv(const double* __restrict__ in, int pitch, int kx, int u0, in
 }
 
 template <int R>
-__global__ void __launch_bounds__(K3M_NT, 2) k3l2_szmap_kernel(const __grid_constant__ k3_args a) {
+__global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_constant__ k3_args a) {
     extern __shared__ __align__(128) unsigned char k3m_raw[];
     constexpr int P = 256 * R, Q = P / 2 + 1, NT = K3M_NT;
     const jx_dev& d = a.d;
@@ -281,9 +283,15 @@ __global__ void __launch_bounds__(K3M_NT, 2) k3l2_szmap_kernel(const __grid_cons
 
 }  // namespace
 
+// Used for the cyclic length 1024 (measured on B200, 8 192 walkers: 19.6 -> 15.3 ms per 4 096-walker launch at 511
+// pixels); at 512 it only ties k3l_szmap_kernel<2> (2.73 against 2.70 ms: the 128-register budget of 512 threads costs
+// spills that eat the occupancy gain), so that size stays on the older kernel unless JX_K3L2=2 asks for this one.
 bool jx_szmap_large2_ok(const jx_dev& d) {
-    if (const char* e = getenv("JX_K3L2")) if (!atoi(e)) return false;
-    return (d.npad == 512 || d.npad == 1024) && d.bmix && d.nbeam <= K3M_NB && k3m_make_layout(d).total <= 115712;
+    int mode = 1;
+    if (const char* e = getenv("JX_K3L2")) mode = atoi(e);
+    if (mode == 0) return false;
+    if (d.npad == 512 && mode < 2) return false;
+    return (d.npad == 512 || d.npad == 1024) && d.bmix && d.nbeam <= K3M_NB && k3m_make_layout(d).total <= 232448;
 }
 
 size_t jx_szmap_large2_smem_bytes(const jx_dev& d) { return k3m_make_layout(d).total; }
@@ -296,14 +304,14 @@ cudaError_t jx_szmap_large2_configure(const jx_dev& d) {
     return e;
 }
 
-// scratch / scratch2: [min(W, 2 sm_count)][hp8][xs_pitch] doubles each
+// scratch / scratch2: [min(W, sm_count)][hp8][xs_pitch] doubles each
 cudaError_t jx_launch_szmap_large2(const jx_dev& d, const double* coef, const uint32_t* flags, int W, int sm_count,
                                    double* convq, double* tri, double* scratch, double* scratch2, cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
     k3_args a;
     a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.tri = tri; a.scratch = scratch; a.scratch2 = scratch2;
     const size_t smem = k3m_make_layout(d).total;
-    const int grid = W < 2 * sm_count ? W : 2 * sm_count;
+    const int grid = W < sm_count ? W : sm_count;
     if (d.npad == 512)
         k3l2_szmap_kernel<2><<<grid, K3M_NT, smem, st>>>(a);
     else
