@@ -377,6 +377,7 @@ def run_secondary(name, world, rank, local, dist, args, barrier, reduce_max, poo
                "parity_inf_mask_equal": bool(np.array_equal(fin, np.isfinite(gpu_ll))),
                "state_checksum": chk, "setup_s": t_build,
                "peak_memory_gb": torch.cuda.max_memory_allocated() / 1e9}
+    sampler.close()
     eng.close()
     del sampler, eng
     torch.cuda.empty_cache()
@@ -630,6 +631,7 @@ def run_gpu_arm(args):
                                  "sample": f"{sample_n} walkers of the same ensemble, literal per-walker oracle path, "
                                            f"Pool({cores}), {cpu_dt:.1f} s"},
                 "parity_max_abs_dll_vs_cpu_sample": parity}
+    sampler.close()             # the captured iteration (with its collectives) goes before the process group does
     eng.close()
     del sampler, eng
     torch.cuda.empty_cache()

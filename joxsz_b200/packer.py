@@ -79,6 +79,21 @@ class PackedSetup:
     the struct is in use)."""
 
     def __init__(self, fit, max_walkers=1024, device=0):
+        # The constant operators are products / solves done by BLAS / LAPACK, whose summation order depends on the number
+        # of threads the library runs with -- and that differs between a plain `python` process (all cores) and the
+        # ranks `torchrun` starts (OMP_NUM_THREADS=1).  Operators that differ in the last bit make the log-likelihoods
+        # of the same walker differ in the last bit between a 1-GPU and an N-GPU run (seen on hardware as a
+        # `state_checksum` mismatch), which breaks the bit-identity of the chains.  Packing is therefore single-threaded.
+        try:
+            from threadpoolctl import threadpool_limits
+            ctx = threadpool_limits(limits=1)
+        except Exception:                      # pragma: no cover - threadpoolctl is a dependency of scipy's wheels
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            self._pack(fit, max_walkers, device)
+
+    def _pack(self, fit, max_walkers, device):
         pars = fit.pars
         thawed = list(fit.thawed)
         sz = fit.data.sz

@@ -478,6 +478,20 @@ class EnsembleSampler:
     def graph_active(self):
         return self._graph is not None
 
+    def release_graph(self):
+        """Drop the captured iteration (it is re-captured on the next step).  Call it before
+        ``torch.distributed.destroy_process_group()``: a live CUDA graph that holds captured NCCL collectives keeps the
+        communicator busy and the teardown waits for it forever."""
+        if self._graph is not None:
+            torch.cuda.synchronize(self.device)
+            self._graph = None
+            self._iter_dev_value = None
+
+    def close(self):
+        """Release the graph and the peer-memory buffers (end of a multi-process run)."""
+        self.release_graph()
+        self._px = None
+
     def launches_per_step(self, kernels_per_loglike=6):
         """Kernels of this library launched (or replayed) per ensemble iteration on this rank."""
         n = 2 * (kernels_per_loglike + self.ops.launches_per_half_step) + getattr(self.ops, "launches_per_permutation", 0)

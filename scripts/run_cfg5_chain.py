@@ -121,6 +121,7 @@ def main():
                 "cpu_baseline": {"value": cpu_rate, "unit": "evals/s", "cores": cores, "kind": "port",
                                  "sample": f"{len(theta)} walkers, literal per-walker oracle path, {cpu_dt:.1f} s"}}
         print(json.dumps(line), flush=True)
+    mcmc.close()
     eng.close()
     if world > 1:
         dist.barrier()

@@ -118,3 +118,19 @@ def test_unsupported_geometry_is_rejected(cl1226_fit):
     bad.data.sz.integ_sig = 0.0
     with pytest.raises(PackError):
         PackedSetup(bad)
+
+
+def test_packing_does_not_depend_on_blas_threads(cl1226_fit):
+    """The operators must come out bit-identical whatever thread count BLAS runs with: a `python` process (all cores)
+    and the ranks torchrun starts (OMP_NUM_THREADS=1) otherwise disagree in the last bit of proj_op, and with it in
+    the last bit of log-likelihoods -- found on hardware as a state_checksum mismatch between 1 and 2 GPUs."""
+    import threadpoolctl
+    from joxsz_b200.packer import PackedSetup
+    packs = []
+    for n in (1, 2, 5):
+        with threadpoolctl.threadpool_limits(n):
+            packs.append(PackedSetup(cl1226_fit, max_walkers=16, device=0))
+    for k in ("proj_op", "y_op", "w_integ", "g_op", "w_t0", "bhat", "bmix", "hf", "cmat", "dinv"):
+        a = np.asarray(getattr(packs[0], k))
+        for other in packs[1:]:
+            assert np.array_equal(a.view(np.int64), np.asarray(getattr(other, k)).view(np.int64)), k

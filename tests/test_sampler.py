@@ -343,6 +343,7 @@ def _nccl_worker(rank, world, port, W, steps, graph, exchange, q):
         s.step()
     q.put((rank, s.coords_host(), s.log_prob_host(), s.acceptance_fraction, s.graph_active, s._graph_failed,
            s._px is not None))
+    s.close()                  # the captured iteration holds NCCL collectives: it goes before the process group
     dist.barrier()
     eng.close()
     dist.destroy_process_group()
