@@ -255,3 +255,33 @@ def test_collapsed_mode_matches_staged_and_golden(cl1226_fit, golden):
     assert np.max(np.abs(b[fin] - golden["ll"][fin])) < 1e-6
     assert not np.isnan(b).any()
     staged.close(); coll.close()
+
+
+@pytest.mark.gpu
+def test_loglike_bits_do_not_depend_on_the_batch(cl1226_fit):
+    """A walker's log-likelihood is bit-identical whatever batch it is evaluated in -- sizes around the persistent grid
+    of the map kernel (148 CTAs, two walkers in flight each), with skipped (flagged) walkers in between -- and equal to the
+    K3 form of the map stage (JX_K3_WS=0 engine).  The N-GPU chain is the 1-GPU chain only because of this."""
+    import os
+    from joxsz_b200.batched import BatchedLikelihood
+    from joxsz_b200.synthetic import draw_parameters
+    theta = draw_parameters(cl1226_fit.thawed, n=600, seed=31, spread=0.03, frac_bad=0.2)
+    eng = BatchedLikelihood(cl1226_fit, max_walkers=600)
+    full = eng(theta)
+    assert np.isinf(full).sum() > 50 and np.isfinite(full).sum() > 300
+    for n in (1, 2, 3, 147, 148, 149, 295, 296, 297, 445, 599):
+        part = eng(theta[:n])
+        assert np.array_equal(part.view(np.int64), full[:n].view(np.int64)), n
+        tail = eng(theta[600 - n:])
+        assert np.array_equal(tail.view(np.int64), full[600 - n:].view(np.int64)), n
+    old = os.environ.get("JX_K3_WS")
+    os.environ["JX_K3_WS"] = "0"
+    try:
+        eng0 = BatchedLikelihood(cl1226_fit, max_walkers=600)
+    finally:
+        if old is None:
+            del os.environ["JX_K3_WS"]
+        else:
+            os.environ["JX_K3_WS"] = old
+    assert np.array_equal(eng0(theta).view(np.int64), full.view(np.int64))
+    eng.close(); eng0.close()
