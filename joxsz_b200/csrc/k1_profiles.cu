@@ -11,7 +11,9 @@
 
 namespace {
 
-constexpr int K1_WARPS = 8;
+// warps (= walkers) per CTA: 8 for large batches; 4 for the small per-rank batches of a multi-GPU step, where 8-walker CTAs
+// leave the SMs unevenly loaded (4 096 walkers = 512 CTAs on 148 SMs: 3 or 4 per SM)
+constexpr int K1_WARPS = 8, K1_WARPS_SMALL = 4, K1_SMALL_BATCH = 16384;
 
 struct k1_args {
     jx_dev d;
@@ -21,11 +23,12 @@ struct k1_args {
     uint32_t* flags;
 };
 
-__global__ void __launch_bounds__(K1_WARPS * 32, 4) k1_profiles_kernel(const __grid_constant__ k1_args a) {
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 32 / NW) k1_profiles_kernel(const __grid_constant__ k1_args a) {
     extern __shared__ double k1_smem[];
     const jx_dev& d = a.d;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = blockIdx.x * K1_WARPS + warp;
+    const int w = blockIdx.x * NW + warp;
     double* mass_s = k1_smem + (size_t)warp * (d.nr + JX_NPAR + 1);
     double* par_s = mass_s + d.nr;
     if (w >= a.W) return;   // whole warp leaves together; no block-level barrier below
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 4) k1_profiles_kernel(const __g
 
     // the radius-independent quantities of the walker are the same for every lane: one copy per warp in shared memory
     // (broadcast loads) instead of 26 doubles of registers per thread, which buys a third CTA per SM
-    __shared__ jx_walker_pars wp_all[K1_WARPS];
+    __shared__ jx_walker_pars wp_all[NW];
     if (lane == 0) wp_all[warp] = jx_prepare(par_s, d.dens_mode);
     __syncwarp();
     const jx_walker_pars& wp = wp_all[warp];
@@ -144,7 +147,10 @@ __global__ void __launch_bounds__(256) k_radial_kernel(const __grid_constant__ k
 cudaError_t jx_profiles_configure(const jx_dev& d) {
     const size_t smem = (size_t)K1_WARPS * (d.nr + JX_NPAR + 1) * sizeof(double);
     if (smem <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(k1_profiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k1_profiles_kernel<K1_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k1_profiles_kernel<K1_WARPS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return e;
 }
 
 cudaError_t jx_launch_profiles(const jx_dev& d, const double* theta, int W, double* pp, int ld_pp, double* tsz,
@@ -152,9 +158,15 @@ cudaError_t jx_launch_profiles(const jx_dev& d, const double* theta, int W, doub
                                cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
     k1_args a{d, theta, W, ld_pp, pp, tsz, ne_ann, tx_ann, prior, cint, flags};
-    size_t smem = (size_t)K1_WARPS * (d.nr + JX_NPAR + 1) * sizeof(double);
-    int blocks = (W + K1_WARPS - 1) / K1_WARPS;
-    k1_profiles_kernel<<<blocks, K1_WARPS * 32, smem, st>>>(a);
+    if (W <= K1_SMALL_BATCH) {
+        constexpr int NW = K1_WARPS_SMALL;
+        const size_t smem = (size_t)NW * (d.nr + JX_NPAR + 1) * sizeof(double);
+        k1_profiles_kernel<NW><<<(W + NW - 1) / NW, NW * 32, smem, st>>>(a);
+    } else {
+        constexpr int NW = K1_WARPS;
+        const size_t smem = (size_t)NW * (d.nr + JX_NPAR + 1) * sizeof(double);
+        k1_profiles_kernel<NW><<<(W + NW - 1) / NW, NW * 32, smem, st>>>(a);
+    }
     return cudaGetLastError();
 }
 
