@@ -21,20 +21,20 @@
 
 namespace {
 
-constexpr int K3M_NT = 512;                         // threads per CTA: 32 transform groups, 16 warps, one CTA per SM
+constexpr int K3M_NT_A = 512, K3M_NT_B = 384, K3M_NT_C = 256;       // threads per CTA (one CTA per SM): 16 warps at 128 registers, or 12 at 168
 constexpr int K3M_NB = JX_BMIX_ROWS, K3M_UB = 16, K3M_PF = 8;
 
 struct k3m_layout {
     size_t tw, twp, xbuf, coef, mbar, total;
 };
 
-__host__ __device__ inline k3m_layout k3m_make_layout(const jx_dev& d) {
+__host__ __device__ inline k3m_layout k3m_make_layout(const jx_dev& d, int nthreads) {
     k3m_layout L;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~size_t(15); return at; };
     L.tw = take(256 * sizeof(double2));
     L.twp = take((size_t)d.npad * sizeof(double2));
-    L.xbuf = take((size_t)(K3M_NT / 16) * JX_XB_ELEMS * sizeof(double2));
+    L.xbuf = take((size_t)(nthreads / 16) * JX_XB_ELEMS * sizeof(double2));
     L.coef = take((size_t)d.ncoef * sizeof(double));
     L.mbar = take(sizeof(uint64_t));
     L.total = o;
@@ -136,13 +136,13 @@ JX_D void k3m_yconv(const double* __restrict__ in, int pitch, int kx, int u0, in
     }
 }
 
-template <int R>
+template <int R, int K3M_NT>
 __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_constant__ k3_args a) {
     extern __shared__ __align__(128) unsigned char k3m_raw[];
     constexpr int P = 256 * R, Q = P / 2 + 1, NT = K3M_NT;
     const jx_dev& d = a.d;
     const int H = d.nh, hp8 = d.hp8;
-    const k3m_layout L = k3m_make_layout(d);
+    const k3m_layout L = k3m_make_layout(d, K3M_NT);
     double2* tw_s = reinterpret_cast<double2*>(k3m_raw + L.tw);
     double2* twp_s = reinterpret_cast<double2*>(k3m_raw + L.twp);
     double2* xbuf_all = reinterpret_cast<double2*>(k3m_raw + L.xbuf);
@@ -283,6 +283,14 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
 
 }  // namespace
 
+static int k3m_threads() {
+    if (const char* e = getenv("JX_K3L2_NT")) {
+        if (atoi(e) == K3M_NT_B) return K3M_NT_B;
+        if (atoi(e) == K3M_NT_C) return K3M_NT_C;
+    }
+    return K3M_NT_A;
+}
+
 // Used for the cyclic length 1024 (measured on B200, 8 192 walkers: 19.6 -> 15.3 ms per 4 096-walker launch at 511
 // pixels); at 512 it only ties k3l_szmap_kernel<2> (2.73 against 2.70 ms: the 128-register budget of 512 threads costs
 // spills that eat the occupancy gain), so that size stays on the older kernel unless JX_K3L2=2 asks for this one.
@@ -291,17 +299,25 @@ bool jx_szmap_large2_ok(const jx_dev& d) {
     if (const char* e = getenv("JX_K3L2")) mode = atoi(e);
     if (mode == 0) return false;
     if (d.npad == 512 && mode < 2) return false;
-    return (d.npad == 512 || d.npad == 1024) && d.bmix && d.nbeam <= K3M_NB && k3m_make_layout(d).total <= 232448;
+    return (d.npad == 512 || d.npad == 1024) && d.bmix && d.nbeam <= K3M_NB && k3m_make_layout(d, k3m_threads()).total <= 232448;
 }
 
-size_t jx_szmap_large2_smem_bytes(const jx_dev& d) { return k3m_make_layout(d).total; }
+size_t jx_szmap_large2_smem_bytes(const jx_dev& d) { return k3m_make_layout(d, k3m_threads()).total; }
+
+template <class F>
+static auto k3m_dispatch(const jx_dev& d, F&& f) {
+    const int nt = k3m_threads();
+    if (d.npad == 512)
+        return nt == K3M_NT_A ? f(k3l2_szmap_kernel<2, K3M_NT_A>, nt)
+             : nt == K3M_NT_B ? f(k3l2_szmap_kernel<2, K3M_NT_B>, nt) : f(k3l2_szmap_kernel<2, K3M_NT_C>, nt);
+    return nt == K3M_NT_A ? f(k3l2_szmap_kernel<4, K3M_NT_A>, nt)
+         : nt == K3M_NT_B ? f(k3l2_szmap_kernel<4, K3M_NT_B>, nt) : f(k3l2_szmap_kernel<4, K3M_NT_C>, nt);
+}
 
 cudaError_t jx_szmap_large2_configure(const jx_dev& d) {
-    const int smem = (int)k3m_make_layout(d).total;
-    cudaError_t e = d.npad == 512
-        ? cudaFuncSetAttribute(k3l2_szmap_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-        : cudaFuncSetAttribute(k3l2_szmap_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    return e;
+    return k3m_dispatch(d, [&](auto kern, int nt) {
+        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3m_make_layout(d, nt).total);
+    });
 }
 
 // scratch / scratch2: [min(W, sm_count)][hp8][xs_pitch] doubles each
@@ -310,11 +326,9 @@ cudaError_t jx_launch_szmap_large2(const jx_dev& d, const double* coef, const ui
     if (W <= 0) return cudaSuccess;
     k3_args a;
     a.d = d; a.coef = coef; a.flags = flags; a.W = W; a.convq = convq; a.tri = tri; a.scratch = scratch; a.scratch2 = scratch2;
-    const size_t smem = k3m_make_layout(d).total;
     const int grid = W < sm_count ? W : sm_count;
-    if (d.npad == 512)
-        k3l2_szmap_kernel<2><<<grid, K3M_NT, smem, st>>>(a);
-    else
-        k3l2_szmap_kernel<4><<<grid, K3M_NT, smem, st>>>(a);
-    return cudaGetLastError();
+    return k3m_dispatch(d, [&](auto kern, int nt) {
+        kern<<<grid, nt, k3m_make_layout(d, nt).total, st>>>(a);
+        return cudaGetLastError();
+    });
 }

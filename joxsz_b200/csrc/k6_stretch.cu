@@ -168,9 +168,9 @@ k6_accept_p2p_kernel(const double* __restrict__ coords, const double* __restrict
             }
         }
     }
-    __threadfence_system();                    // this thread's stores are visible to every GPU before the CTA reports
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    __syncthreads();                           // the CTA's stores are ordered before thread 0's fence (cumulativity):
+    if (threadIdx.x == 0) {                    // one system-scope fence per CTA instead of one per thread
+        __threadfence_system();
         const unsigned int prev = atomicAdd(done, 1u);
         if (prev == gridDim.x - 1) {           // last CTA of the grid: every row of this rank has been written
             *done = 0u;
