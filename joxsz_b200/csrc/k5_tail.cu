@@ -16,7 +16,7 @@
 
 namespace {
 
-constexpr int K5_WARPS = 8;
+constexpr int K5_WARPS = 8, K5_WARPS_SMALL = 2, K5_SMALL_BATCH = 16384;     // walkers per CTA: fewer for small batches (even SM load)
 
 struct k5_args {
     jx_dev d;
@@ -37,11 +37,12 @@ JX_D double linear_extrap(double x, const double* __restrict__ xk, const double*
     return slope * (x - x0) + y0;
 }
 
-__global__ void __launch_bounds__(K5_WARPS * 32) k5_tail_kernel(const __grid_constant__ k5_args a) {
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) k5_tail_kernel(const __grid_constant__ k5_args a) {
     extern __shared__ double k5_smem[];
     const jx_dev& d = a.d;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = blockIdx.x * K5_WARPS + warp;
+    const int w = blockIdx.x * NW + warp;
     if (w >= a.W) return;                       // whole warps leave; no block barrier below
     const int H = d.nh;
     double* bright_s = k5_smem + (size_t)warp * H;
@@ -111,7 +112,12 @@ cudaError_t jx_launch_tail(const jx_dev& d, const double* theta, const double* r
                            double* row_out, cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
     k5_args a{d, theta, row, tsz, prior, xlike, cint, flags, W, ld_row, nparts, bright, model, chisq, ll, row_out};
-    const size_t smem = (size_t)K5_WARPS * d.nh * sizeof(double);
-    k5_tail_kernel<<<(W + K5_WARPS - 1) / K5_WARPS, K5_WARPS * 32, smem, st>>>(a);
+    if (W <= K5_SMALL_BATCH) {
+        constexpr int NW = K5_WARPS_SMALL;
+        k5_tail_kernel<NW><<<(W + NW - 1) / NW, NW * 32, (size_t)NW * d.nh * sizeof(double), st>>>(a);
+    } else {
+        constexpr int NW = K5_WARPS;
+        k5_tail_kernel<NW><<<(W + NW - 1) / NW, NW * 32, (size_t)NW * d.nh * sizeof(double), st>>>(a);
+    }
     return cudaGetLastError();
 }
