@@ -8,9 +8,10 @@
 // of P/2+1 complex samples per 16-thread group) fill the shared memory of an SM with one 256-thread CTA.  Here
 //   * a row transform reads its samples straight from the L2-resident scratch map and writes its spectrum straight to
 //     the other scratch map (out of place: A1 xs -> xc, B xc -> xs, C xs -> packed triangle), so a group only needs
-//     its 4 KB exchange tile: one CTA of 512 threads per SM at 128 registers (16 warps per SM instead of 8, and still
-//     one scratch-map pair per SM: two CTAs per SM would double the working set and push it out of the 126 MB L2 --
-//     measured: L2 hit rate 79 % -> 69 %, 6 GB of DRAM traffic per launch, slower);
+//     its 4 KB exchange tile: one CTA of 384 threads per SM at 168 registers (12 warps per SM instead of 8 at 255 pixels
+//     and of 5 at 511, and still one scratch-map pair per SM: two CTAs per SM would double the working set and push it
+//     out of the 126 MB L2 -- measured: L2 hit rate 79 % -> 69 %, 6 GB of DRAM traffic per launch, slower; 512 threads
+//     at 128 registers spill more than the extra warps give back);
 //   * the y convolution takes 16 rows per thread (16 accumulators + 28 taps in 128 registers);
 //   * at P = 1024 the s = 3 branch of the radix-4 decimation is never computed: its spectrum samples are the mirror
 //     images X[P - K] of the s = 1 branch (every sequence of the stage is even), which stores both (-25 % of the
@@ -284,21 +285,19 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
 }  // namespace
 
 static int k3m_threads() {
+    // measured on B200 (8 192 walkers, ms per 4 096-walker launch at 255 / 511 pixels): 512 threads 2.73 / 15.33,
+    // 384 threads 2.62 / 15.13, 256 threads 2.69 / 15.62 -- 168 registers per thread spill least
     if (const char* e = getenv("JX_K3L2_NT")) {
-        if (atoi(e) == K3M_NT_B) return K3M_NT_B;
+        if (atoi(e) == K3M_NT_A) return K3M_NT_A;
         if (atoi(e) == K3M_NT_C) return K3M_NT_C;
     }
-    return K3M_NT_A;
+    return K3M_NT_B;
 }
 
-// Used for the cyclic length 1024 (measured on B200, 8 192 walkers: 19.6 -> 15.3 ms per 4 096-walker launch at 511
-// pixels); at 512 it only ties k3l_szmap_kernel<2> (2.73 against 2.70 ms: the 128-register budget of 512 threads costs
-// spills that eat the occupancy gain), so that size stays on the older kernel unless JX_K3L2=2 asks for this one.
+// Measured on B200 against k3l_szmap_kernel (8 192 walkers, per 4 096-walker launch): 511 pixels 19.6 -> 15.1 ms,
+// 255 pixels 2.70 -> 2.62 ms.  JX_K3L2=0 selects the older kernel.
 bool jx_szmap_large2_ok(const jx_dev& d) {
-    int mode = 1;
-    if (const char* e = getenv("JX_K3L2")) mode = atoi(e);
-    if (mode == 0) return false;
-    if (d.npad == 512 && mode < 2) return false;
+    if (const char* e = getenv("JX_K3L2")) if (!atoi(e)) return false;
     return (d.npad == 512 || d.npad == 1024) && d.bmix && d.nbeam <= K3M_NB && k3m_make_layout(d, k3m_threads()).total <= 232448;
 }
 
