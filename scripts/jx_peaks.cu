@@ -10,14 +10,20 @@
 
 namespace {
 __global__ void fp64_peak_kernel(double* out, int iters) {
-    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
-           a7 = a0 + 7;
+    // 16 independent chains per thread, both multiplicands constant (register reuse cache): the pattern that reaches the
+    // highest DFMA rate on B200 (36.3 TFLOP/s; 8 chains give 34.8) -- see scripts/dfma_pattern_microbench.cu
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = threadIdx.x * 1e-9 + i;
     const double m = 1.0000001, c = 1e-7;
     for (int i = 0; i < iters; ++i) {
-        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = fma(a[k], m, c);
     }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += a[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 __global__ void dmma_peak_kernel(double* out, int iters) {
     double c[8][2];
@@ -89,7 +95,7 @@ extern "C" int jxp_measure_fp64_tflops(int32_t device, double* tflops) {
         cudaEventSynchronize(e1);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        double tf = 2.0 * 16.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
         if (tf > best) best = tf;
     }
     cudaEventDestroy(e0);
