@@ -29,11 +29,18 @@
 
 namespace {
 
-constexpr int K7_BM = 128, K7_BK = 32, K7_LDS = K7_BK + 4, K7_STAGES = 3;
-#ifndef K7_WARPS
-#define K7_WARPS 16         // 16 warps x (8 x 8 NT) or 8 warps x (16 x 8 NT)
-#endif
-constexpr int K7_THREADS = 32 * K7_WARPS, K7_MT = K7_BM / (8 * K7_WARPS);   // DMMA row tiles per warp
+// Two tilings.  Narrow quarter planes (at most 11 DMMA column tiles, the shipped 171-pixel maps): 8 warps x (16 x 8 NT),
+// K chunks of 16, 104 KB of shared memory -> two CTAs per SM, one computing while the other fills its ring or stores
+// (measured at the shipped geometry: 0.74 -> 0.68 ms per 32 768 walkers, 0.84 of the DMMA peak).  Wide ones (255 / 511
+// pixels) need the whole SM for one CTA: 16 warps x (8 x 8 NT), K chunks of 32.
+constexpr int K7_BM = 128, K7_STAGES = 3;
+constexpr int K7_NT_TWO_CTAS = 11;
+template <int NT> struct k7_cfg {
+    static constexpr bool two = NT <= K7_NT_TWO_CTAS;
+    static constexpr int WARPS = two ? 8 : 16, BK = two ? 16 : 32, CTAS = two ? 2 : 1;
+    static constexpr int LDS = BK + 4, THREADS = 32 * WARPS, MT = K7_BM / (8 * WARPS);
+    static constexpr size_t SMEM = (size_t)K7_STAGES * (K7_BM + 8 * NT) * LDS * sizeof(double);
+};
 
 JX_D void k7_cp16(void* smem, const void* gmem, bool valid) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -50,16 +57,17 @@ JX_D void k7_dmma(double& c0, double& c1, double a, double b) {
 }
 
 template <int NT>
-constexpr size_t k7_smem_bytes() { return (size_t)K7_STAGES * (K7_BM + 8 * NT) * K7_LDS * sizeof(double); }
+constexpr size_t k7_smem_bytes() { return k7_cfg<NT>::SMEM; }
 
 // A: [M, lda] packed convolved maps (lda = K rounded up to 32, zero padded), B: [ldc, lda] = R^T zero padded,
 // C: [kparts][M][ldc]; blockIdx.z selects a block of 8 NT output columns (quarter planes wider than 136 pixels)
 template <int NT>
-__global__ void __launch_bounds__(K7_THREADS, 1)
+__global__ void __launch_bounds__(k7_cfg<NT>::THREADS, k7_cfg<NT>::CTAS)
 k7_filter_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int lda, int ldc,
                       int M, int nchunks_total, int chunks_per_part) {
     extern __shared__ __align__(16) double k7_smem[];
     constexpr int BN = 8 * NT;
+    constexpr int K7_BK = k7_cfg<NT>::BK, K7_LDS = k7_cfg<NT>::LDS, K7_THREADS = k7_cfg<NT>::THREADS, K7_MT = k7_cfg<NT>::MT;
     double* As = k7_smem;                                          // [STAGES][BM][LDS]
     double* Bs = k7_smem + (size_t)K7_STAGES * K7_BM * K7_LDS;     // [STAGES][BN][LDS]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -72,7 +80,7 @@ k7_filter_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B
 #pragma unroll
         for (int it = 0; it < (K7_BM * K7_BK / 2) / K7_THREADS; ++it) {
             const int piece = it * K7_THREADS + tid;
-            const int row = piece >> 4, col = (piece & 15) * 2;
+            const int row = piece / (K7_BK / 2), col = (piece % (K7_BK / 2)) * 2;
             const bool ok = m0 + row < M;
             k7_cp16(As + ((size_t)stage * K7_BM + row) * K7_LDS + col, A + (size_t)(ok ? m0 + row : 0) * lda + k0 + col, ok);
         }
@@ -80,7 +88,7 @@ k7_filter_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B
         for (int it = 0; it < (BN * K7_BK / 2 + K7_THREADS - 1) / K7_THREADS; ++it) {
             const int piece = it * K7_THREADS + tid;
             if (piece < BN * K7_BK / 2) {
-                const int row = piece >> 4, col = (piece & 15) * 2;
+                const int row = piece / (K7_BK / 2), col = (piece % (K7_BK / 2)) * 2;
                 k7_cp16(Bs + ((size_t)stage * BN + row) * K7_LDS + col, B + (size_t)(n0 + row) * lda + k0 + col, true);
             }
         }
@@ -167,20 +175,22 @@ cudaError_t jx_filter_configure(const jx_dev& d) {
 // JX_FILTER_CPP chunks of 32, at most 9 parts (longer parts for the larger maps).  117 chunks -> 9 parts of 13 for
 // the shipped cluster: 256 walker tiles x 9 parts fill 148 SMs to 97 %.
 int jx_filter_parts(const jx_dev& d) {
-    const int nchunks = d.ktri / K7_BK, p = (nchunks + JX_FILTER_CPP - 1) / JX_FILTER_CPP;
+    const int nchunks = d.ktri / 32, p = (nchunks + JX_FILTER_CPP - 1) / JX_FILTER_CPP;      // parts are counted in 32-wide chunks
     return p < 9 ? p : 9;
 }
 
 // rowp[kparts][W][hpf] = partial sums of tri[W, ktri] . filt_op[hpf, ktri]^T
 cudaError_t jx_launch_filter(const jx_dev& d, const double* tri, int W, double* rowp, cudaStream_t st) {
     if (W <= 0) return cudaSuccess;
-    const int nchunks = d.ktri / K7_BK, parts = jx_filter_parts(d), cpp = (nchunks + parts - 1) / parts;
+    // part boundaries in units of 32 packed pixels whatever the kernel's own chunk width: the summation order of a
+    // walker's row (and with it every bit of its log-likelihood) does not depend on the tiling
+    const int nchunks32 = d.ktri / 32, parts = jx_filter_parts(d), cpp32 = (nchunks32 + parts - 1) / parts;
     int nblk, nt;
     jx_filter_tiling(d.hp8, &nblk, &nt);
     dim3 grid(parts, (W + K7_BM - 1) / K7_BM, nblk);
     switch (nt) {
-#define K7_CASE(n) case n: k7_filter_gemm_kernel<n><<<grid, K7_THREADS, k7_smem_bytes<n>(), st>>>( \
-                               tri, d.filt_op, rowp, d.ktri, d.hpf, W, nchunks, cpp); break;
+#define K7_CASE(n) case n: k7_filter_gemm_kernel<n><<<grid, k7_cfg<n>::THREADS, k7_smem_bytes<n>(), st>>>( \
+                               tri, d.filt_op, rowp, d.ktri, d.hpf, W, d.ktri / k7_cfg<n>::BK, cpp32 * (32 / k7_cfg<n>::BK)); break;
         K7_FOR_NT(K7_CASE)
 #undef K7_CASE
         default: return cudaErrorInvalidValue;
