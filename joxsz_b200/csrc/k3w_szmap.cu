@@ -196,6 +196,9 @@ __global__ void __launch_bounds__(KW_NT, 1) k3w_szmap_kernel(const __grid_consta
                 double* tri0 = tri_w + (u0 * H - ((u0 * (u0 - 1)) >> 1) - u0);     // + v
                 double* tri1 = tri0 + (H - u0 - 1);
                 if (tapq) __syncwarp();          // exchange tile read by every lane before the in-place tap stores
+                // straight from the registers: staging the rows in shared memory for coalesced 256-byte stores was
+                // measured slower (C phase 13.3 k -> 15.5 k cycles per walker: the extra shared-memory traffic costs more
+                // than the partial-sector stores)
 #pragma unroll
                 for (int p = 0; p < 16; ++p) {
                     const int n = t + 16 * rev16(p);
@@ -366,8 +369,7 @@ __global__ void __launch_bounds__(KW_NT, 1) k3w_szmap_kernel(const __grid_consta
                 const int u0 = (2 * pass + rsel) * KW_UB;
 #pragma unroll
                 for (int k = 0; k < KW_UB; ++k) acc[k] = 0.0;
-#pragma unroll
-                for (int ii = 0; ii < KW_UB + 2 * (KW_NB - 1); ++ii) {
+                auto taps_of_row = [&](int ii) {
                     const int up = u0 - (KW_NB - 1) + ii, ua = up < 0 ? -up : up;
                     const double x = ua < H ? xs[ua * KW_XS + kx] : 0.0;
 #pragma unroll
@@ -375,6 +377,16 @@ __global__ void __launch_bounds__(KW_NT, 1) k3w_szmap_kernel(const __grid_consta
                         const int j = ii - (KW_NB - 1) - k < 0 ? k + (KW_NB - 1) - ii : ii - (KW_NB - 1) - k;
                         if (j < KW_NB) acc[k] = fma(tap[j], x, acc[k]);
                     }
+                };
+                // Two straight-line segments with ONE warp-uniform branch between them: the input rows of the second
+                // segment lie beyond the map (all zero) for the top row group, a third of its FMAs.  (A test per input
+                // row instead keeps the loads from being scheduled ahead of the FMAs: measured 3.04 -> 3.25 ms.)
+                constexpr int KW_SP = KW_UB + KW_NB - 3;
+#pragma unroll
+                for (int ii = 0; ii < KW_SP; ++ii) taps_of_row(ii);
+                if (u0 - (KW_NB - 1) + KW_SP < H) {
+#pragma unroll
+                    for (int ii = KW_SP; ii < KW_UB + 2 * (KW_NB - 1); ++ii) taps_of_row(ii);
                 }
                 if (pass == 0) {                 // park the first pass in tensor memory (columns 64..111)
                     uint32_t ra[32], rb[16];
