@@ -188,7 +188,7 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
     d.nr = s->nr; d.nrp = (s->nr + 7) & ~7; d.nt = s->nt; d.nmap = s->nmap; d.nh = s->nh; d.npad = s->npad;
     d.nq = s->npad / 2 + 1; d.nseg = s->nseg; d.ncoef = 4 * s->nseg;
     d.hp8 = (s->nh + 7) & ~7; d.hp16 = (s->nh + 15) & ~15;
-    d.xs_pitch = ((d.nq > d.hp16 ? d.nq : d.hp16) + 1) & ~1;
+    d.xs_pitch = ((d.nq > d.hp16 ? d.nq : d.hp16) + 3) & ~3;       // rows start on a 32-byte sector
     d.nconv = s->nconv; d.nd = s->nd; d.na = s->na; d.nb = s->nb; d.ntab = s->ntab;
     d.tmin = s->tmin; d.tmax = s->tmax; d.max_walkers = s->max_walkers;
     d.calc_integ = s->calc_integ ? 1 : 0; d.integ_mu = s->integ_mu; d.integ_sig = s->integ_sig;

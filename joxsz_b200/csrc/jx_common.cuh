@@ -59,7 +59,7 @@ struct jx_dev {
     const double* filt_q;    // [nh, nh]
     // derived at jx_create
     int hp8, hp16;           // nh rounded up to 8 / 16
-    int xs_pitch;            // large-map path: doubles per row of the per-CTA scratch map (even, >= nq and hp16)
+    int xs_pitch;            // large-map path: doubles per row of the per-CTA scratch map (multiple of 4, >= nq and hp16)
     double* ws_scratch;      // large-map path: [sm_count][hp8][xs_pitch]
     double* ws_scratch2;     // large-map path, direct y convolution: its output map, same shape
     const uint16_t* seg16;   // [nh, nh] seg narrowed

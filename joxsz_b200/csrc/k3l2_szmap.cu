@@ -20,10 +20,31 @@
 //     convolution run (they are only read by the synthesis).
 #include "k3_common.cuh"
 
+#ifdef JX_K3_CLOCKS
+__device__ unsigned long long jx_k3l2_clk[8];
+extern "C" int jx_debug_k3l2_clocks(unsigned long long* out8) {
+    cudaError_t e = cudaMemcpyFromSymbol(out8, jx_k3l2_clk, sizeof(jx_k3l2_clk));
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(jx_k3l2_clk, z, sizeof(z));
+    return e == cudaSuccess ? 0 : -1;
+}
+#define K3M_CLK_DECL long long k3_t0 = clock64()
+#define K3M_CLK(i) do { if (threadIdx.x == 0) { long long k3_t1 = clock64(); atomicAdd(&jx_k3l2_clk[i], (unsigned long long)(k3_t1 - k3_t0)); k3_t0 = k3_t1; } } while (0)
+#else
+#define K3M_CLK_DECL
+#define K3M_CLK(i)
+#endif
+
 namespace {
 
 constexpr int K3M_NT_A = 512, K3M_NT_B = 384, K3M_NT_C = 256;       // threads per CTA (one CTA per SM): 16 warps at 128 registers, or 12 at 168
-constexpr int K3M_NB = JX_BMIX_ROWS, K3M_UB = 16, K3M_PF = 8;
+#ifndef K3M_PF_N
+#define K3M_PF_N 8
+#endif
+#ifndef K3M_UB_N
+#define K3M_UB_N 32
+#endif
+constexpr int K3M_NB = JX_BMIX_ROWS, K3M_UB = K3M_UB_N, K3M_PF = K3M_PF_N;      // taps, rows per task, loads in flight
 
 struct k3m_layout {
     size_t tw, twp, xbuf, coef, mbar, total;
@@ -58,30 +79,32 @@ JX_D void mul_wr2(double& r, double& i, int e) {
 // X[K] for every K <= P/2 exactly once.  Radix-R decimation in frequency around the register FFT-256:
 //   y_s[m] = w_P^(s m) sum_j x[m + 256 j] w_R^(s j),   X[R k + s] = FFT256(y_s)[k];
 // for R = 4 the branch s = 3 is skipped: X[4 k + 3] = X[P - 4 k - 3] = X[4 (255 - k) + 1] comes out of branch s = 1.
-template <int R, class LD, class ST>
-JX_D void k3m_group_fft_even(int t, unsigned gmask, LD&& ld, ST&& st, const double2* __restrict__ tw256,
+template <int R, class LD, class STV, class ST1>
+JX_D void k3m_group_fft_even(int t, unsigned gmask, LD&& ld, STV&& stv, ST1&& st1, const double2* __restrict__ tw256,
                              const double2* __restrict__ twp, double2* __restrict__ xbuf) {
     constexpr int P = 256 * R, NS = R == 4 ? 3 : R;
-    double re[16], im[16];
-#pragma unroll 1
-    for (int s = 0; s < NS; ++s) {
-        // the gather runs in chunks of G samples: all loads of a chunk are in flight together (L2 latency), and the
-        // compiler barrier between chunks keeps it from hoisting every load of the line (the kernel lives in 128
-        // registers: two CTAs per SM)
-        constexpr int G = 8 / R;
+    // The line is gathered ONCE for all branches (it used to be re-read from L2 per branch: the load latency of
+    // 16 / G dependent chunks per branch was most of a row transform): 32 NS registers hold the branch inputs, then
+    // the register FFT-256 runs branch after branch.  Same operations in the same order per output as before.
+    double re[NS][16], im[NS][16];
+    // the gather runs in chunks of G samples: all loads of a chunk are in flight together (L2 latency), and the
+    // compiler barrier between chunks keeps it from hoisting every load of the line
+    constexpr int G = 8 / R;
 #pragma unroll
-        for (int j0 = 0; j0 < 16; j0 += G) {
-            double2 v[G][R];
+    for (int j0 = 0; j0 < 16; j0 += G) {
+        double2 v[G][R];
 #pragma unroll
-            for (int g = 0; g < G; ++g)
+        for (int g = 0; g < G; ++g)
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const int n = t + 16 * (j0 + g) + 256 * j;
-                    v[g][j] = ld(n <= P / 2 ? n : P - n);
-                }
+            for (int j = 0; j < R; ++j) {
+                const int n = t + 16 * (j0 + g) + 256 * j;
+                v[g][j] = ld(n <= P / 2 ? n : P - n);
+            }
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const int m = t + 16 * (j0 + g);
+        for (int g = 0; g < G; ++g) {
+            const int m = t + 16 * (j0 + g);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
                 double ar = 0.0, ai = 0.0;
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
@@ -95,20 +118,34 @@ JX_D void k3m_group_fft_even(int t, unsigned gmask, LD&& ld, ST&& st, const doub
                     ai = ar * w.y + ai * w.x;
                     ar = tr;
                 }
-                re[j0 + g] = ar; im[j0 + g] = ai;
+                re[s][j0 + g] = ar; im[s][j0 + g] = ai;
             }
-            asm volatile("" ::: "memory");
         }
-        fft256_pass1(t, re, im, tw256, xbuf);
-        __syncwarp(gmask);
-        fft256_pass2(t, re, im, xbuf);
-        __syncwarp(gmask);
+        asm volatile("" ::: "memory");
+    }
 #pragma unroll
-        for (int p = 0; p < 16; ++p) {
-            const int K = R * (t + 16 * rev16(p)) + s;
-            if (K <= P / 2) st(K, re[p], im[p]);
-            else if (R == 4 && s == 1) st(P - K, re[p], im[p]);        // the s = 3 samples, by evenness
+    for (int s = 0; s < NS; ++s) {
+        fft256_pass1(t, re[s], im[s], tw256, xbuf);
+        __syncwarp(gmask);
+        fft256_pass2(t, re[s], im[s], xbuf);
+        __syncwarp(gmask);
+    }
+    // Position p of branch s holds X[R k + s], k = t + 16 rev16(p): a thread owns R consecutive samples of the
+    // spectrum (for R = 4 the s = 3 sample X[4 k + 3] = X[P - 4 k - 3] = X[4 (255 - k) + 1] sits at position 15 - p of
+    // branch 1 in lane 15 - t: one shuffle), and stores them as one 16 R-byte run instead of R scattered 8-byte
+    // stores at a 8 R-byte stride (which cost the row transforms of the 1024-point maps a third of their time).
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+        double vr[R], vi[R];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) { vr[s] = re[s][p]; vi[s] = im[s][p]; }
+        if constexpr (R == 4) {
+            vr[3] = __shfl_xor_sync(gmask, re[1][15 - p], 15);
+            vi[3] = __shfl_xor_sync(gmask, im[1][15 - p], 15);
         }
+        const int k = t + 16 * rev16(p);
+        if (k < 128) stv(R * k, vr, vi);
+        else if (k == 128) st1(P / 2, vr[0], vi[0]);
     }
 }
 
@@ -181,6 +218,7 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
     for (int w = w_first; w < a.W; w += gridDim.x, ++it) {
         // only the bits the profile kernel wrote decide the skip (see k3_szmap.cu)
         const bool skip = a.flags && (a.flags[w] & ~(uint32_t)JX_FLAG_XNONPOS) != 0u;
+        K3M_CLK_DECL;
         mbar_wait(mbar, (uint32_t)(it & 1));
         if (!skip) {
             // ---- A0: synthesise the quarter-plane map (u <= v listed, mirrored on store)
@@ -212,6 +250,7 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
             }
         }
         if (skip) continue;
+        K3M_CLK(0);
 
         // ---- A1: rows along x, xs -> xc
         for (int rp = grp; rp < npair; rp += ngroups) {
@@ -224,14 +263,24 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
             k3m_group_fft_even<R>(
                 t, gmask,
                 [&](int f) { return f < H ? make_double2(__ldcg(r0 + f), has1 ? __ldcg(r1 + f) : 0.0) : make_double2(0.0, 0.0); },
+                [&](int K0, const double (&vr)[R], const double (&vi)[R]) {
+#pragma unroll
+                    for (int i = 0; i < R; i += 2) {
+                        __stcg(reinterpret_cast<double2*>(o0 + K0 + i), make_double2(vr[i], vr[i + 1]));
+                        if (has1) __stcg(reinterpret_cast<double2*>(o1 + K0 + i), make_double2(vi[i], vi[i + 1]));
+                    }
+                },
                 [&](int K, double vr, double vi) { __stcg(o0 + K, vr); if (has1) __stcg(o1 + K, vi); },
                 tw_s, twp_s, xbuf);
         }
         __syncthreads();
+        K3M_CLK(1);
 
         // ---- B: 55-tap convolution along y, xc -> xs; lane = column, tasks of 16 rows x 32 columns
         {
-            const int ncw = (Q + 31) >> 5, nrb = (H + K3M_UB - 1) / K3M_UB, ntask = ncw * nrb, nw = NT >> 5;
+            // the Q - 1 = P / 2 columns below the Nyquist frequency make whole 32-column blocks; the Nyquist column
+            // follows with lane = row (as a 33rd column block it cost a whole row of tasks for one active lane)
+            const int ncw = (Q - 1) >> 5, nrb = (H + K3M_UB - 1) / K3M_UB, ntask = ncw * nrb, nw = NT >> 5;
             const int t_lo = (int)(((long)warp * ntask) / nw), t_hi = (int)(((long)(warp + 1) * ntask) / nw);
             double tap[K3M_NB];
             int cw_have = -1;
@@ -251,8 +300,24 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
                 for (int k = 0; k < K3M_UB; ++k)
                     if (on && u0 + k < H) __stcg(xs + (size_t)(u0 + k) * pitch + kx, acc[k]);
             }
+            // Nyquist column: one output row per lane, inputs and taps in the order of k3m_yconv
+            const double* tn = d.bmix + (Q - 1);
+            for (int r0 = 32 * (nw - 1 - warp); r0 < H; r0 += 32 * nw) {
+                const int r = r0 + lane;
+                double acc = 0.0;
+                if (r < H) {
+#pragma unroll 5
+                    for (int dd = -(K3M_NB - 1); dd <= K3M_NB - 1; ++dd) {
+                        const int up = r + dd, ua = up < 0 ? -up : up;
+                        const double x = ua < H ? __ldcg(xc + (size_t)ua * pitch + (Q - 1)) : 0.0;
+                        acc = fma(__ldg(tn + (size_t)(dd < 0 ? -dd : dd) * d.bmix_pitch), x, acc);
+                    }
+                    __stcg(xs + (size_t)r * pitch + (Q - 1), acc);
+                }
+            }
         }
         __syncthreads();
+        K3M_CLK(2);
 
         // ---- C: rows back to pixel space, xs -> packed triangle (and the quarter-plane tap)
         double* cq = a.convq ? a.convq + (size_t)w * H * H : nullptr;
@@ -266,32 +331,46 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
             k3m_group_fft_even<R>(
                 t, gmask,
                 [&](int f) { return make_double2(__ldcg(r0 + f), has1 ? __ldcg(r1 + f) : 0.0); },
+                [&](int v0, const double (&vr)[R], const double (&vi)[R]) {
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        const int v = v0 + i;
+                        if (v < H) {
+                            if (v >= u0) tri0[v] = vr[i];
+                            if (has1 && v >= u1) tri1[v] = vi[i];
+                            if (cq) {
+                                cq[(size_t)u0 * H + v] = vr[i];
+                                if (has1) cq[(size_t)u1 * H + v] = vi[i];
+                            }
+                        }
+                    }
+                },
                 [&](int v, double vr, double vi) {
-                    if (v < H) {
+                    if (v < H) {                 // never with a real beam (P >= 2 H - 1 + beam - 1), kept for safety
                         if (v >= u0) tri0[v] = vr;
                         if (has1 && v >= u1) tri1[v] = vi;
-                        if (cq) {
-                            cq[(size_t)u0 * H + v] = vr;
-                            if (has1) cq[(size_t)u1 * H + v] = vi;
-                        }
+                        if (cq) { cq[(size_t)u0 * H + v] = vr; if (has1) cq[(size_t)u1 * H + v] = vi; }
                     }
                 },
                 tw_s, twp_s, xbuf);
         }
         __syncthreads();        // every read of xs is done before the next walker's synthesis overwrites it
+        K3M_CLK(3);
     }
 }
 
 }  // namespace
 
 static int k3m_threads() {
-    // measured on B200 (8 192 walkers, ms per 4 096-walker launch at 255 / 511 pixels): 512 threads 2.73 / 15.33,
-    // 384 threads 2.62 / 15.13, 256 threads 2.69 / 15.62 -- 168 registers per thread spill least
+    // measured on B200 (ms per 4 096-walker launch at 255 / 511 pixels) before the line gather was merged over the
+    // branches: 512 threads 2.73 / 15.33, 384 threads 2.62 / 15.13, 256 threads 2.69 / 15.62.  With 32 NS live
+    // registers of branch inputs the transforms want the 255-register budget: 256 threads are the default now
+    // (cycles per walker at 255 / 511 pixels: 145 k / 830 k against 213 k / 1 086 k with 384 threads)
     if (const char* e = getenv("JX_K3L2_NT")) {
         if (atoi(e) == K3M_NT_A) return K3M_NT_A;
-        if (atoi(e) == K3M_NT_C) return K3M_NT_C;
+        if (atoi(e) == K3M_NT_B) return K3M_NT_B;
     }
-    return K3M_NT_B;
+    return K3M_NT_C;
 }
 
 // Measured on B200 against k3l_szmap_kernel (8 192 walkers, per 4 096-walker launch): 511 pixels 19.6 -> 15.1 ms,

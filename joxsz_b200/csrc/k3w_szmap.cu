@@ -41,6 +41,20 @@ extern "C" int jx_debug_k3w_clocks(unsigned long long* out8) {
 #define K3W_CLK(i)
 #endif
 
+// Developer experiment (scripts/k3_phase_clocks.py with JX_CLK_DEFS): -DJX_K3W_NO_F / -DJX_K3W_NO_M build the kernel
+// with one warp group doing no work of its own (it keeps the barrier protocol), to time the other group alone.  The
+// results of such a build are meaningless.
+#ifdef JX_K3W_NO_F
+#define KW_F_FIRST(x) (1 << 20)
+#else
+#define KW_F_FIRST(x) (x)
+#endif
+#ifdef JX_K3W_NO_M
+#define KW_M_ON (a.W < 0)
+#else
+#define KW_M_ON true
+#endif
+
 namespace {
 
 constexpr int KW_NT = 512, KW_NG = 256;      // CTA size, threads per group
@@ -177,7 +191,7 @@ __global__ void __launch_bounds__(KW_NT, 1) k3w_szmap_kernel(const __grid_consta
             double* xs = maps + (size_t)pb * map_stride;
             double* tri_w = a.tri + (size_t)pw * d.ktri;
             double re[16], im[16];
-            for (int base = gw * 3; base < npair; base += 24) {
+            for (int base = KW_F_FIRST(gw * 3); base < npair; base += 24) {
                 tmem_ld32(tm_mine + 64, twr);
                 const bool on = lane_on && base + fg < npair;
                 const int u0 = 2 * (base + fg < npair ? base + fg : npair - 1), u1 = u0 + 1;
@@ -259,7 +273,7 @@ __global__ void __launch_bounds__(KW_NT, 1) k3w_szmap_kernel(const __grid_consta
                         tmem_ld64(tm_mine, r);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int k = 0; k < KW_SYN; ++k) {
+                        for (int k = KW_F_FIRST(0); k < KW_SYN; ++k) {
                             const int ez = (int)r[4 * k + 2], ew = (int)r[4 * k + 3];
                             const int sg = ez & 0xffff, u = (ez >> 16) & 0xffff, v = ew & 0xffff;
                             if (u != 0xffff) {
@@ -274,7 +288,7 @@ __global__ void __launch_bounds__(KW_NT, 1) k3w_szmap_kernel(const __grid_consta
                     // ---------------- A1: rows along x, in place, exchanging inside the row pair
                     {
                         double re[16], im[16];
-                        for (int base = gw * 3; base < npair; base += 24) {
+                        for (int base = KW_F_FIRST(gw * 3); base < npair; base += 24) {
                             tmem_ld32(tm_mine + 64, twr);
                             const bool on = lane_on && base + fg < npair;
                             const int u0 = 2 * (base + fg < npair ? base + fg : npair - 1), u1 = u0 + 1;
@@ -348,7 +362,7 @@ __global__ void __launch_bounds__(KW_NT, 1) k3w_szmap_kernel(const __grid_consta
 #pragma unroll
             for (int rd = 0; rd < 2; ++rd) {
                 const int nu = (rd * 8 + gw) * 6 + (lane & 7);
-                const bool non = (lane & 7) < 6 && nu < H;
+                const bool non = KW_M_ON && (lane & 7) < 6 && nu < H;
                 double acc = 0.0;
                 if (non) {
                     const double* col = xs + 128;
@@ -365,7 +379,7 @@ __global__ void __launch_bounds__(KW_NT, 1) k3w_szmap_kernel(const __grid_consta
             }
             double acc[KW_UB];
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
+            for (int pass = KW_M_ON ? 0 : 2; pass < 2; ++pass) {
                 const int u0 = (2 * pass + rsel) * KW_UB;
 #pragma unroll
                 for (int k = 0; k < KW_UB; ++k) acc[k] = 0.0;

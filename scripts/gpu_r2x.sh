@@ -1,0 +1,9 @@
+#!/bin/bash
+# K3L2: 32- / 64-row convolution tasks, Nyquist column apart
+mkdir -p gpurun_out
+JX_K3L2_NT=256 timeout 400 python -m pytest tests/test_large_maps.py -m gpu -x -q > gpurun_out/pytest_x.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_x.log
+for tag in _ub32 _ub64; do for nt in 256 384; do for wl in synth255 synth511; do
+  [ $tag = _ub64 ] && [ $nt = 384 ] && continue
+  JX_K3L2_NT=$nt JX_CLK_TAG=$tag JX_CLK_WORKLOAD=$wl timeout 120 python scripts/k3_phase_clocks.py 4096 > gpurun_out/k3l2_clocks_${wl}${tag}_nt$nt.log 2>&1
+  echo "== $wl $tag nt=$nt"; tail -5 gpurun_out/k3l2_clocks_${wl}${tag}_nt$nt.log | tr '\n' ' '; echo
+done; done; done
