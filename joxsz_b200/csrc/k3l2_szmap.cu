@@ -38,16 +38,19 @@ extern "C" int jx_debug_k3l2_clocks(unsigned long long* out8) {
 namespace {
 
 constexpr int K3M_NT_A = 512, K3M_NT_B = 384, K3M_NT_C = 256;       // threads per CTA (one CTA per SM): 16 warps at 128 registers, or 12 at 168
-#ifndef K3M_PF_N
-#define K3M_PF_N 8
-#endif
 #ifndef K3M_UB_N
-#define K3M_UB_N 32
+#define K3M_UB_N 16
 #endif
-constexpr int K3M_NB = JX_BMIX_ROWS, K3M_UB = K3M_UB_N, K3M_PF = K3M_PF_N;      // taps, rows per task, loads in flight
+constexpr int K3M_NB = JX_BMIX_ROWS, K3M_UB = K3M_UB_N;      // taps, rows per convolution task
+constexpr int K3M_TILES = 4;                                 // tile buffers of the y convolution, at most
+
+// a convolution tile: H rows of 32 spectrum samples, one row of zeros (stands for every row beyond the map), and the
+// 28 tap rows of its 32 columns
+__host__ __device__ constexpr int k3m_tile_rows(int H) { return H + 1 + K3M_NB; }
 
 struct k3m_layout {
-    size_t tw, twp, xbuf, coef, mbar, total;
+    size_t tw, twp, coef, nyq, mbar, xbuf, total;
+    int ntile;               // [H][32] tiles of the y convolution that fit the arena (exchange tiles and what is left)
 };
 
 __host__ __device__ inline k3m_layout k3m_make_layout(const jx_dev& d, int nthreads) {
@@ -55,10 +58,18 @@ __host__ __device__ inline k3m_layout k3m_make_layout(const jx_dev& d, int nthre
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~size_t(15); return at; };
     L.tw = take(256 * sizeof(double2));
-    L.twp = take((size_t)d.npad * sizeof(double2));
-    L.xbuf = take((size_t)(nthreads / 16) * JX_XB_ELEMS * sizeof(double2));
+    L.twp = take((size_t)(d.npad / 2) * sizeof(double2));
     L.coef = take((size_t)d.ncoef * sizeof(double));
+    L.nyq = take((size_t)(d.nh + 1 + K3M_NB) * sizeof(double));      // Nyquist column, a zero, its taps
     L.mbar = take(sizeof(uint64_t));
+    o = (o + 127) & ~size_t(127);
+    // the arena: exchange tiles of the transform groups in A1 / C, ring of convolution tiles in B
+    L.xbuf = take((size_t)(nthreads / 16) * JX_XB_ELEMS * sizeof(double2));
+    const size_t tile = (size_t)k3m_tile_rows(d.nh) * 32 * sizeof(double), cap = 232448;
+    size_t n = cap > L.xbuf ? (cap - L.xbuf) / tile : 0;
+    if (n > K3M_TILES) n = K3M_TILES;
+    L.ntile = (int)n;
+    if (L.xbuf + n * tile > o) o = L.xbuf + n * tile;
     L.total = o;
     return L;
 }
@@ -113,7 +124,7 @@ JX_D void k3m_group_fft_even(int t, unsigned gmask, LD&& ld, STV&& stv, ST1&& st
                     ar += vr; ai += vi;
                 }
                 if (s) {
-                    const double2 w = twp[(s * m) & (P - 1)];
+                    const double2 w = twp[s * m];
                     const double tr = ar * w.x - ai * w.y;
                     ai = ar * w.y + ai * w.x;
                     ar = tr;
@@ -149,23 +160,25 @@ JX_D void k3m_group_fft_even(int t, unsigned gmask, LD&& ld, STV&& stv, ST1&& st
     }
 }
 
-// y convolution of UB consecutive rows of column kx (same scheme and summation order as k3l_szmap.cu / k3_szmap.cu)
-JX_D void k3m_yconv(const double* __restrict__ in, int pitch, int kx, int u0, int H, const double (&tap)[K3M_NB],
+JX_D void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+JX_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+JX_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// y convolution of UB consecutive rows of one column of a shared-memory tile (lane = column); row H of the tile is
+// zero and stands for every row beyond the map, so the loads carry no predicate.  Same scheme and summation order as
+// k3l_szmap.cu / k3_szmap.cu
+JX_D void k3m_yconv(const double* __restrict__ tile, int lane, int u0, int H, const double (&tap)[K3M_NB],
                     double (&acc)[K3M_UB]) {
     constexpr int NIN = K3M_UB + 2 * (K3M_NB - 1);
-    auto fetch = [&](int ii) {
-        const int up = u0 - (K3M_NB - 1) + ii, ua = up < 0 ? -up : up;
-        return ua < H ? __ldcg(in + (size_t)ua * pitch + kx) : 0.0;
-    };
 #pragma unroll
     for (int k = 0; k < K3M_UB; ++k) acc[k] = 0.0;
-    double xq[K3M_PF];
-#pragma unroll
-    for (int q = 0; q < K3M_PF; ++q) xq[q] = fetch(q);
 #pragma unroll
     for (int ii = 0; ii < NIN; ++ii) {
-        const double x = xq[ii % K3M_PF];
-        if (ii + K3M_PF < NIN) xq[ii % K3M_PF] = fetch(ii + K3M_PF);
+        const int up = u0 - (K3M_NB - 1) + ii, ua = up < 0 ? -up : up;
+        const double x = tile[(ua < H ? ua : H) * 32 + lane];
 #pragma unroll
         for (int k = 0; k < K3M_UB; ++k) {
             const int j = ii - (K3M_NB - 1) - k < 0 ? k + (K3M_NB - 1) - ii : ii - (K3M_NB - 1) - k;
@@ -197,7 +210,7 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
     double* xc = a.scratch2 + (size_t)blockIdx.x * hp8 * pitch;     // row spectra
 
     for (int i = tid; i < 256; i += NT) fft256_make_twiddle(i, tw_s[i]);
-    for (int i = tid; i < P; i += NT) {
+    for (int i = tid; i < P / 2; i += NT) {          // s m < P / 2 for the branches that are computed: half a turn
         const double ang = -2.0 * 3.14159265358979323846 * (double)i / (double)P;
         twp_s[i] = make_double2(cos(ang), sin(ang));
     }
@@ -223,13 +236,17 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
         if (!skip) {
             // ---- A0: synthesise the quarter-plane map (u <= v listed, mirrored on store)
             const int4* tab = reinterpret_cast<const int4*>(d.synth);
-            for (int base = 0; base < d.nsynth; base += 8 * NT) {
-                int4 e[8];
+            auto tab_load = [&](int base, int4 (&e)[8]) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int i = base + k * NT + tid;
                     e[k] = i < d.nsynth ? __ldg(tab + i) : make_int4(0, 0, 0xffff0000, 0);
                 }
+            };
+            int4 e[8], en[8];
+            tab_load(0, e);
+            for (int base = 0; base < d.nsynth; base += 8 * NT) {
+                if (base + 8 * NT < d.nsynth) tab_load(base + 8 * NT, en);       // the next batch is in flight
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int sg = e[k].z & 0xffff, u = (e[k].z >> 16) & 0xffff, v = e[k].w & 0xffff;
@@ -239,6 +256,8 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
                         __stcg(xs + (size_t)v * pitch + u, z);
                     }
                 }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) e[k] = en[k];
             }
         }
         __syncthreads();                       // the coefficients have been read (or are not needed): refill them
@@ -276,45 +295,74 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
         __syncthreads();
         K3M_CLK(1);
 
-        // ---- B: 55-tap convolution along y, xc -> xs; lane = column, tasks of 16 rows x 32 columns
+        // ---- B: 55-tap convolution along y, xc -> xs.  [H rows x 32 columns] tiles of the row spectra stream through a
+        // ring of shared-memory buffers (cp.async, 16 bytes per thread and copy, up to three tiles ahead of the
+        // arithmetic: a register prefetch queue is never deeper than the six scoreboards of a warp); lane = column,
+        // a warp takes 16-row blocks of the tile
         {
-            // the Q - 1 = P / 2 columns below the Nyquist frequency make whole 32-column blocks; the Nyquist column
-            // follows with lane = row (as a 33rd column block it cost a whole row of tasks for one active lane)
-            const int ncw = (Q - 1) >> 5, nrb = (H + K3M_UB - 1) / K3M_UB, ntask = ncw * nrb, nw = NT >> 5;
-            const int t_lo = (int)(((long)warp * ntask) / nw), t_hi = (int)(((long)(warp + 1) * ntask) / nw);
-            double tap[K3M_NB];
-            int cw_have = -1;
-            for (int task = t_lo; task < t_hi; ++task) {
-                const int cw = task / nrb, u0 = (task % nrb) * K3M_UB;
-                const int kx = 32 * cw + lane;
-                const bool on = kx < Q;
-                const int kxc = on ? kx : Q - 1;
-                if (cw != cw_have) {
-#pragma unroll
-                    for (int j = 0; j < K3M_NB; ++j) tap[j] = __ldg(d.bmix + (size_t)j * d.bmix_pitch + kxc);
-                    cw_have = cw;
+            // the Q - 1 = P / 2 columns below the Nyquist frequency make whole 32-column tiles; the Nyquist column
+            // is done with lane = row (as a tile it would cost a tile's work for one active lane)
+            const int ncw = (Q - 1) >> 5, nrb = (H + K3M_UB - 1) / K3M_UB, nw = NT >> 5;
+            const int ntb = L.ntile, tile_elems = k3m_tile_rows(H) * 32;
+            double* tiles = reinterpret_cast<double*>(k3m_raw + L.xbuf);
+            auto tile_fetch = [&](int cw) {
+                double* dst = tiles + (size_t)(cw % ntb) * tile_elems;
+                const double* src = xc + 32 * cw;
+                for (int i = tid; i < H * 16; i += NT) {
+                    const int r = i >> 4, c = (i & 15) * 2;
+                    cp_async16(dst + r * 32 + c, src + (size_t)r * pitch + c);
                 }
-                double acc[K3M_UB];
-                k3m_yconv(xc, pitch, kxc, u0, H, tap, acc);
-#pragma unroll
-                for (int k = 0; k < K3M_UB; ++k)
-                    if (on && u0 + k < H) __stcg(xs + (size_t)(u0 + k) * pitch + kx, acc[k]);
+                const double* tsrc = d.bmix + 32 * cw;
+                for (int i = tid; i < K3M_NB * 16; i += NT) {
+                    const int r = i >> 4, c = (i & 15) * 2;
+                    cp_async16(dst + (H + 1 + r) * 32 + c, tsrc + (size_t)r * d.bmix_pitch + c);
+                }
+            };
+            for (int i = tid; i < 32 * ntb; i += NT) tiles[(size_t)(i >> 5) * tile_elems + H * 32 + (i & 31)] = 0.0;
+            for (int i = 0; i < ntb - 1; ++i) {          // a group per tile slot, empty or not: uniform counting
+                if (i < ncw) tile_fetch(i);
+                cp_async_commit();
             }
-            // Nyquist column: one output row per lane, inputs and taps in the order of k3m_yconv
-            const double* tn = d.bmix + (Q - 1);
-            for (int r0 = 32 * (nw - 1 - warp); r0 < H; r0 += 32 * nw) {
-                const int r = r0 + lane;
-                double acc = 0.0;
-                if (r < H) {
-#pragma unroll 5
-                    for (int dd = -(K3M_NB - 1); dd <= K3M_NB - 1; ++dd) {
-                        const int up = r + dd, ua = up < 0 ? -up : up;
-                        const double x = ua < H ? __ldcg(xc + (size_t)ua * pitch + (Q - 1)) : 0.0;
-                        acc = fma(__ldg(tn + (size_t)(dd < 0 ? -dd : dd) * d.bmix_pitch), x, acc);
+            // the Nyquist column, a zero behind it and its taps go to shared memory by plain loads
+            double* nyq_s = reinterpret_cast<double*>(k3m_raw + L.nyq);
+            for (int i = tid; i <= H + K3M_NB; i += NT)
+                nyq_s[i] = i < H ? __ldcg(xc + (size_t)i * pitch + (Q - 1))
+                         : i == H ? 0.0 : __ldg(d.bmix + (size_t)(i - H - 1) * d.bmix_pitch + (Q - 1));
+            for (int cw = 0; cw < ncw; ++cw) {
+                // tiles cw + 1 .. cw + ntb - 2 may still be in flight; one barrier per tile: past it tile cw has landed
+                // for every thread and every warp is done with tile cw - 1, whose buffer the next fetch refills
+                if (ntb >= 4) cp_async_wait<2>(); else if (ntb == 3) cp_async_wait<1>(); else cp_async_wait<0>();
+                __syncthreads();
+                if (cw + ntb - 1 < ncw) tile_fetch(cw + ntb - 1);
+                cp_async_commit();
+                if (cw == 0) {
+                    // Nyquist column: one output row per lane (rows dealt over the warps), inputs and taps in the
+                    // order of k3m_yconv
+                    for (int r = warp + nw * lane; r < H; r += nw * 32) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int dd = -(K3M_NB - 1); dd <= K3M_NB - 1; ++dd) {
+                            const int up = r + dd, ua = up < 0 ? -up : up;
+                            acc = fma(nyq_s[H + 1 + (dd < 0 ? -dd : dd)], nyq_s[ua < H ? ua : H], acc);
+                        }
+                        __stcg(xs + (size_t)r * pitch + (Q - 1), acc);
                     }
-                    __stcg(xs + (size_t)r * pitch + (Q - 1), acc);
+                }
+                const int kx = 32 * cw + lane;
+                const double* tile = tiles + (size_t)(cw % ntb) * tile_elems;
+                double tap[K3M_NB];
+#pragma unroll
+                for (int j = 0; j < K3M_NB; ++j) tap[j] = tile[(H + 1 + j) * 32 + lane];
+                for (int rb = warp; rb < nrb; rb += nw) {
+                    const int u0 = rb * K3M_UB;
+                    double acc[K3M_UB];
+                    k3m_yconv(tile, lane, u0, H, tap, acc);
+#pragma unroll
+                    for (int k = 0; k < K3M_UB; ++k)
+                        if (u0 + k < H) __stcg(xs + (size_t)(u0 + k) * pitch + kx, acc[k]);
                 }
             }
+            cp_async_wait<0>();
         }
         __syncthreads();
         K3M_CLK(2);
@@ -377,7 +425,8 @@ static int k3m_threads() {
 // 255 pixels 2.70 -> 2.62 ms.  JX_K3L2=0 selects the older kernel.
 bool jx_szmap_large2_ok(const jx_dev& d) {
     if (const char* e = getenv("JX_K3L2")) if (!atoi(e)) return false;
-    return (d.npad == 512 || d.npad == 1024) && d.bmix && d.nbeam <= K3M_NB && k3m_make_layout(d, k3m_threads()).total <= 232448;
+    return (d.npad == 512 || d.npad == 1024) && d.bmix && d.nbeam <= K3M_NB && k3m_make_layout(d, k3m_threads()).total <= 232448 &&
+           k3m_make_layout(d, k3m_threads()).ntile >= 2;
 }
 
 size_t jx_szmap_large2_smem_bytes(const jx_dev& d) { return k3m_make_layout(d, k3m_threads()).total; }
