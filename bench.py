@@ -275,9 +275,16 @@ def fp64_lane_ops(pk):
         return synth + rows + ycols
     R = P // 256
     synth = (H * (H + 1) // 2) * 4
-    rows = 2 * H * R * 16 * 2 * 230                      # sixteen-thread full-complex FFT-256 x R sub-transforms per row
-    ycols = ((H + 31) // 32 * 32) * Q * (2 * nbeam - 1)
+    ns = 3 if R == 4 else R                              # branches computed (the s = 3 branch of radix 4 is mirrored)
+    rows = 2 * npair * ns * 16 * 2 * 230                 # sixteen-thread full-complex FFT-256 x ns branches per ROW PAIR
+    ycols = ((H + 15) // 16 * 16) * Q * (2 * nbeam - 1)
     return synth + rows + ycols
+
+
+def large_map_kernel_name(pk):
+    """Which kernel jx_create picks for cyclic lengths 512 / 1024 (jx_szmap_large2_ok in csrc/k3l2_szmap.cu)."""
+    k3l2 = os.environ.get("JX_K3L2", "1") != "0" and int(pk.bmix.shape[0]) <= 28
+    return "k3l2_szmap_kernel" if k3l2 else "k3l_szmap_kernel"
 
 
 def note(msg):
@@ -366,7 +373,7 @@ def run_secondary(name, world, rank, local, dist, args, barrier, reduce_max, poo
         out = {"config": workload_config(Wn, world, name), "value": Wn * steps / (ms * 1e-3), "unit": UNIT,
                "ms_per_step": ms / steps, "steps": steps, "timed_blocks": len(blocks),
                "block_ms": [b / steps for b in blocks], "graph": sampler.graph_active,
-               "map_kernel": "k3l_szmap_kernel" if pk.map_ops.P != 256 else "k3_szmap_kernel",
+               "map_kernel": large_map_kernel_name(pk) if pk.map_ops.P != 256 else "k3w_szmap_kernel",
                "stage_ms_per_launch": stage_ms, "walkers_per_launch": nw,
                "map_kernel_fp64_lane_ops_per_walker": lane,
                "map_kernel_fp64_lane_ops_per_s": lane * nw / k3_s if k3_s > 0 else None,
@@ -543,7 +550,7 @@ def run_gpu_arm(args):
         k3_s = (k3_ms / max(k3_n, 1)) * 1e-3
         lane_model = fp64_lane_ops(pk)
         lane, lane_src, tr = lane_model, "counted from the kernel's structure (bench.fp64_lane_ops)", None
-        map_kernel = "k3_szmap_kernel" if pk.map_ops.P == 256 else "k3l_szmap_kernel"
+        map_kernel = "k3_szmap_kernel" if pk.map_ops.P == 256 else large_map_kernel_name(pk)
         try:
             if WORKLOAD == "cl1226":
                 tr = json.load(open(os.path.join(ROOT, "profiles", "k3_ncu_traffic.json")))

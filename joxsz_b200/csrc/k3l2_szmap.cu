@@ -1,23 +1,35 @@
-// K3L2 -- the large-map stage (cyclic length 512 / 1024, direct y convolution) re-laid-out for occupancy.
+// K3L2 -- the large-map stage (cyclic length 512 / 1024, direct y convolution).
 //
 // Same mathematics and phases as k3l_szmap.cu (reference joxsz_funcs.py:462-464) -- results identical at P = 512 and
-// equal within rounding at P = 1024 (a quarter of the spectrum samples is taken from its mirror image) -- with a
-// different resource plan.  ncu on k3l_szmap_kernel<2> (profiles/
-// r02a_k3l255_ncu_summary.txt): 8 warps per SM at 255 registers, FP64 pipe 33 % busy, 0.46 eligible warps per
-// cycle -- the kernel waits on its own dependency chains because the staging lines of the row transforms (two lines
-// of P/2+1 complex samples per 16-thread group) fill the shared memory of an SM with one 256-thread CTA.  Here
-//   * a row transform reads its samples straight from the L2-resident scratch map and writes its spectrum straight to
-//     the other scratch map (out of place: A1 xs -> xc, B xc -> xs, C xs -> packed triangle), so a group only needs
-//     its 4 KB exchange tile: one CTA of 384 threads per SM at 168 registers (12 warps per SM instead of 8 at 255 pixels
-//     and of 5 at 511, and still one scratch-map pair per SM: two CTAs per SM would double the working set and push it
-//     out of the 126 MB L2 -- measured: L2 hit rate 79 % -> 69 %, 6 GB of DRAM traffic per launch, slower; 512 threads
-//     at 128 registers spill more than the extra warps give back);
-//   * the y convolution takes 16 rows per thread (16 accumulators + 28 taps in 128 registers);
+// equal within rounding at P = 1024 (a quarter of the spectrum samples is taken from its mirror image).  The map of a
+// walker (128 x 257 or 256 x 513 doubles) does not fit the shared memory of an SM, so the phases go out of place
+// between two per-CTA scratch maps that are reused walker after walker and stay in the 126 MB L2 at 255 pixels
+// (A1 xs -> xc, B xc -> xs, C xs -> packed triangle); one CTA of 256 threads per SM at 255 registers.
+//   * A row transform (16-thread group, radix-R decimation in frequency around the register FFT-256) gathers its line
+//     ONCE for all branches -- it used to be re-read from L2 per branch, 16 / G dependent chunks of loads each -- and
+//     keeps the 32 NS branch inputs in registers, hence the 255-register budget (256 threads: cycles per walker
+//     145 k / 830 k at 255 / 511 pixels against 213 k / 1 086 k with 384 threads at 168 registers).
+//   * A thread ends a transform with R consecutive samples of the spectrum (branch s of position p holds
+//     X[R k + s]; at R = 4 the s = 3 sample comes from lane 15 - t by one shuffle) and stores them as one 16 R-byte run:
+//     the scattered 8-byte stores at an 8 R-byte stride cost the 1024-point row transforms a fifth of their time.
+//   * The y convolution works on [H rows x 32 columns] tiles of the row spectra that all threads stream into a ring of
+//     up to four shared-memory buffers with cp.async (16 bytes per thread and copy; each buffer also receives the 28
+//     tap rows of its columns and keeps a row of zeros that stands for every row beyond the map, so the inner loop
+//     has no predicate), one __syncthreads per tile; a warp convolves 16-row blocks from shared memory as the
+//     256-point kernels do.  Loads straight from L2 into a register queue were bound by the six scoreboards of a warp
+//     (a queue of 16 was no faster than one of 8).  Measured and NOT kept: the same tiles fetched with one
+//     cp.async.bulk per 256-byte row (4 096 requests per walker at 511 pixels: request-rate bound, B 318 k -> 438 k
+//     cycles), and row pairs of the transforms staged by cp.async.bulk behind the previous FFT (A1 34 k -> 49 k).
+//   * The Nyquist column (the 257th / 513th) is convolved apart from shared memory, one output row per lane: as a 33rd
+//     tile it cost a tile's work for one active lane.
 //   * at P = 1024 the s = 3 branch of the radix-4 decimation is never computed: its spectrum samples are the mirror
-//     images X[P - K] of the s = 1 branch (every sequence of the stage is even), which stores both (-25 % of the
-//     transform work);
+//     images X[P - K] of the s = 1 branch (every sequence of the stage is even) (-25 % of the transform work);
 //   * the spline coefficients of the next walker arrive by TMA bulk copy while the current walker's transforms and
-//     convolution run (they are only read by the synthesis).
+//     convolution run (they are only read by the synthesis); the synthesis keeps the next batch of table entries in
+//     flight.
+// Phase clocks per walker on B200 (scripts/k3_phase_clocks.py, JX_CLK_WORKLOAD=synth255 / synth511), first version ->
+// now: 255 pixels A0 13.8 k, A1 48.7 k, B 73.9 k, C 46.4 k = 183 k -> 14.7 / 34.3 / 62.4 / 32.0 = 143 k cycles;
+// 511 pixels 66 / 391 / 315 / 311 = 1 083 k -> 63-80 / 194-213 / 243-252 / 183-204 = 693-739 k.
 #include "k3_common.cuh"
 
 #ifdef JX_K3_CLOCKS

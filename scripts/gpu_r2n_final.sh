@@ -15,4 +15,4 @@ print("e2e", d["e2e"]["value"], "numpy", d["e2e_numpy"]["value"], "collapsed", d
 for k, v in d["secondary"].items():
     print(k, {kk: v.get(kk) for kk in ("value", "ms_per_step", "parity_max_abs_dll_vs_cpu_sample", "error")}, v.get("stage_ms_per_launch", {}).get("szmap"))
 PY
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02c_launches.csv python bench.py --no-secondary --steps 2 --warmup 1 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02g_launches.csv python bench.py --no-secondary --steps 2 --warmup 1 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
