@@ -56,9 +56,12 @@ constexpr int K3M_NT_A = 512, K3M_NT_B = 384, K3M_NT_C = 256;       // threads p
 constexpr int K3M_NB = JX_BMIX_ROWS, K3M_UB = K3M_UB_N;      // taps, rows per convolution task
 constexpr int K3M_TILES = 4;                                 // tile buffers of the y convolution, at most
 
-// a convolution tile: H rows of 32 spectrum samples, one row of zeros (stands for every row beyond the map), and the
-// 28 tap rows of its 32 columns
-__host__ __device__ constexpr int k3m_tile_rows(int H) { return H + 1 + K3M_NB; }
+// a convolution tile of 32 columns: the 27 mirrored rows -27 .. -1 (copies of rows 27 .. 1), the H rows of the map, 27
+// rows of zeros (the rows beyond the map), then the 28 tap rows of its columns.  Every input of every output row is
+// then physically present at tile row (27 + its row): the inner loop loads with immediate offsets and no index
+// arithmetic (|row|, row < H ? ... cost six integer instructions per load, 45 % of the loop)
+constexpr int K3M_PAD = K3M_NB - 1;
+__host__ __device__ constexpr int k3m_tile_rows(int H) { return H + 2 * K3M_PAD + K3M_NB; }
 
 struct k3m_layout {
     size_t tw, twp, coef, nyq, mbar, xbuf, total;
@@ -179,21 +182,19 @@ JX_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memor
 template <int N>
 JX_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// y convolution of UB consecutive rows of one column of a shared-memory tile (lane = column); row H of the tile is
-// zero and stands for every row beyond the map, so the loads carry no predicate.  Same scheme and summation order as
-// k3l_szmap.cu / k3_szmap.cu
-JX_D void k3m_yconv(const double* __restrict__ tile, int lane, int u0, int H, const double (&tap)[K3M_NB],
-                    double (&acc)[K3M_UB]) {
-    constexpr int NIN = K3M_UB + 2 * (K3M_NB - 1);
+// y convolution of UB consecutive rows (from u0) of one column of a shared-memory tile (lane = column): input row
+// u0 - 27 + ii sits at tile row u0 + ii.  Same scheme and summation order as k3l_szmap.cu / k3_szmap.cu
+JX_D void k3m_yconv(const double* __restrict__ tile, int lane, int u0, const double (&tap)[K3M_NB], double (&acc)[K3M_UB]) {
+    constexpr int NIN = K3M_UB + 2 * K3M_PAD;
+    const double* in = tile + u0 * 32 + lane;
 #pragma unroll
     for (int k = 0; k < K3M_UB; ++k) acc[k] = 0.0;
 #pragma unroll
     for (int ii = 0; ii < NIN; ++ii) {
-        const int up = u0 - (K3M_NB - 1) + ii, ua = up < 0 ? -up : up;
-        const double x = tile[(ua < H ? ua : H) * 32 + lane];
+        const double x = in[ii * 32];
 #pragma unroll
         for (int k = 0; k < K3M_UB; ++k) {
-            const int j = ii - (K3M_NB - 1) - k < 0 ? k + (K3M_NB - 1) - ii : ii - (K3M_NB - 1) - k;
+            const int j = ii - K3M_PAD - k < 0 ? k + K3M_PAD - ii : ii - K3M_PAD - k;
             if (j < K3M_NB) acc[k] = fma(tap[j], x, acc[k]);
         }
     }
@@ -308,31 +309,43 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
         K3M_CLK(1);
 
         // ---- B: 55-tap convolution along y, xc -> xs.  [H rows x 32 columns] tiles of the row spectra stream through a
-        // ring of shared-memory buffers (cp.async, 16 bytes per thread and copy, up to three tiles ahead of the
-        // arithmetic: a register prefetch queue is never deeper than the six scoreboards of a warp); lane = column,
-        // a warp takes 16-row blocks of the tile
+        // ring of shared-memory buffers (cp.async, 16 bytes per thread and copy: a register prefetch queue is never
+        // deeper than the six scoreboards of a warp); lane = column, a warp takes a block of K3M_UB rows of a tile.
+        // Rows per block: 16 (K3M_UB).  32-row blocks with two tiles per step (so that every warp still has a block
+        // at 255 pixels) were measured equal (B 62.4 k cycles per walker either way at 255 pixels, 228 k -> 252 k at 511):
+        // the step logic below stays general, the default stays 16.
         {
             // the Q - 1 = P / 2 columns below the Nyquist frequency make whole 32-column tiles; the Nyquist column
             // is done with lane = row (as a tile it would cost a tile's work for one active lane)
             const int ncw = (Q - 1) >> 5, nrb = (H + K3M_UB - 1) / K3M_UB, nw = NT >> 5;
             const int ntb = L.ntile, tile_elems = k3m_tile_rows(H) * 32;
+            int ts = nrb < nw ? nw / nrb : 1;                    // tiles per step
+            if (ntb / ts < 2) ts = 1;
+            const int nslot = ntb / ts, nstep = (ncw + ts - 1) / ts;      // ring slots of ts tiles each; steps
             double* tiles = reinterpret_cast<double*>(k3m_raw + L.xbuf);
-            auto tile_fetch = [&](int cw) {
-                double* dst = tiles + (size_t)(cw % ntb) * tile_elems;
+            auto tile_fetch = [&](int cw, int buf) {
+                double* dst = tiles + (size_t)buf * tile_elems;
                 const double* src = xc + 32 * cw;
-                for (int i = tid; i < H * 16; i += NT) {
-                    const int r = i >> 4, c = (i & 15) * 2;
-                    cp_async16(dst + r * 32 + c, src + (size_t)r * pitch + c);
+                for (int i = tid; i < (H + K3M_PAD) * 16; i += NT) {          // tile rows 0 .. 26 + H <- rows 27 .. 1, 0 .. H - 1
+                    const int tr = i >> 4, c = (i & 15) * 2;
+                    int r = tr - K3M_PAD;
+                    r = r < 0 ? -r : r;
+                    if (r < H) cp_async16(dst + tr * 32 + c, src + (size_t)r * pitch + c);
                 }
                 const double* tsrc = d.bmix + 32 * cw;
                 for (int i = tid; i < K3M_NB * 16; i += NT) {
                     const int r = i >> 4, c = (i & 15) * 2;
-                    cp_async16(dst + (H + 1 + r) * 32 + c, tsrc + (size_t)r * d.bmix_pitch + c);
+                    cp_async16(dst + (H + 2 * K3M_PAD + r) * 32 + c, tsrc + (size_t)r * d.bmix_pitch + c);
                 }
             };
-            for (int i = tid; i < 32 * ntb; i += NT) tiles[(size_t)(i >> 5) * tile_elems + H * 32 + (i & 31)] = 0.0;
-            for (int i = 0; i < ntb - 1; ++i) {          // a group per tile slot, empty or not: uniform counting
-                if (i < ncw) tile_fetch(i);
+            auto step_fetch = [&](int st) {
+                for (int i = 0; i < ts; ++i)
+                    if (st * ts + i < ncw) tile_fetch(st * ts + i, (st % nslot) * ts + i);
+            };
+            for (int i = tid; i < K3M_PAD * 32 * ntb; i += NT)           // the rows beyond the map
+                tiles[(size_t)(i / (K3M_PAD * 32)) * tile_elems + (K3M_PAD + H) * 32 + i % (K3M_PAD * 32)] = 0.0;
+            for (int i = 0; i < nslot - 1; ++i) {        // a group per ring slot, empty or not: uniform counting
+                if (i < nstep) step_fetch(i);
                 cp_async_commit();
             }
             // the Nyquist column, a zero behind it and its taps go to shared memory by plain loads
@@ -340,14 +353,15 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
             for (int i = tid; i <= H + K3M_NB; i += NT)
                 nyq_s[i] = i < H ? __ldcg(xc + (size_t)i * pitch + (Q - 1))
                          : i == H ? 0.0 : __ldg(d.bmix + (size_t)(i - H - 1) * d.bmix_pitch + (Q - 1));
-            for (int cw = 0; cw < ncw; ++cw) {
-                // tiles cw + 1 .. cw + ntb - 2 may still be in flight; one barrier per tile: past it tile cw has landed
-                // for every thread and every warp is done with tile cw - 1, whose buffer the next fetch refills
-                if (ntb >= 4) cp_async_wait<2>(); else if (ntb == 3) cp_async_wait<1>(); else cp_async_wait<0>();
+            for (int st = 0; st < nstep; ++st) {
+                // steps st + 1 .. st + nslot - 2 may still be in flight; one barrier per step: past it the tiles of
+                // step st have landed for every thread and every warp is done with step st - 1, whose slot the next
+                // fetch refills
+                if (nslot >= 4) cp_async_wait<2>(); else if (nslot == 3) cp_async_wait<1>(); else cp_async_wait<0>();
                 __syncthreads();
-                if (cw + ntb - 1 < ncw) tile_fetch(cw + ntb - 1);
+                if (st + nslot - 1 < nstep) step_fetch(st + nslot - 1);
                 cp_async_commit();
-                if (cw == 0) {
+                if (st == 0) {
                     // Nyquist column: one output row per lane (rows dealt over the warps), inputs and taps in the
                     // order of k3m_yconv
                     for (int r = warp + nw * lane; r < H; r += nw * 32) {
@@ -360,15 +374,16 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
                         __stcg(xs + (size_t)r * pitch + (Q - 1), acc);
                     }
                 }
-                const int kx = 32 * cw + lane;
-                const double* tile = tiles + (size_t)(cw % ntb) * tile_elems;
-                double tap[K3M_NB];
+                for (int task = warp; task < ts * nrb; task += nw) {
+                    const int ti = task / nrb, u0 = (task - ti * nrb) * K3M_UB, cw = st * ts + ti;
+                    if (cw >= ncw) continue;
+                    const int kx = 32 * cw + lane;
+                    const double* tile = tiles + (size_t)((st % nslot) * ts + ti) * tile_elems;
+                    double tap[K3M_NB];
 #pragma unroll
-                for (int j = 0; j < K3M_NB; ++j) tap[j] = tile[(H + 1 + j) * 32 + lane];
-                for (int rb = warp; rb < nrb; rb += nw) {
-                    const int u0 = rb * K3M_UB;
+                    for (int j = 0; j < K3M_NB; ++j) tap[j] = tile[(H + 2 * K3M_PAD + j) * 32 + lane];
                     double acc[K3M_UB];
-                    k3m_yconv(tile, lane, u0, H, tap, acc);
+                    k3m_yconv(tile, lane, u0, tap, acc);
 #pragma unroll
                     for (int k = 0; k < K3M_UB; ++k)
                         if (u0 + k < H) __stcg(xs + (size_t)(u0 + k) * pitch + kx, acc[k]);
