@@ -1,8 +1,8 @@
 """Maps larger than the shipped cluster's (BASELINE configs 3 and 5: 512-point grid with a ~256-pixel map,
 1024-point grid with a ~512-pixel map).  The reference can only build odd map sides (2m+1,
 joxsz_main.py:101-103), so the synthetic clusters use 255 and 511 pixels; their cyclic convolution lengths
-are 512 and 1024, which route the map stage to the L2-staged kernel (k3l_szmap.cu).  Parity is against the
-oracle's literal per-walker path on seeded draws."""
+are 512 and 1024, which route the map stage to the large-map kernel (k3l2_szmap.cu; k3l_szmap.cu for wide beams).
+Parity is against the oracle's literal per-walker path on seeded draws."""
 import os
 
 import numpy as np
@@ -47,6 +47,13 @@ def fit201():
     return _build(100, 320)
 
 
+# an odd quarter plane that is not a multiple of the large-map kernel's 16-row blocks (H = 121, cyclic length 512): a
+# last row pair with one row, a partial last block, convolution inputs that run past the zero rows of a tile
+@pytest.fixture(scope="module")
+def fit241():
+    return _build(120, 384)
+
+
 # a beam wider than 55 pixels (FWHM 26"): no direct y convolution, the L2-staged kernel convolves through column FFTs;
 # the quarter plane (H > 136) also takes two column blocks in the filter GEMM
 @pytest.fixture(scope="module")
@@ -59,7 +66,7 @@ def _draws(fit, n, seed, frac_bad=0.1):
     return draw_parameters(fit.thawed, n=n, seed=seed, spread=0.03, frac_bad=frac_bad)
 
 
-@pytest.mark.parametrize("which,P", [("fit141", 256), ("fit201", 256), ("fit255", 512), ("fit511", 1024), ("fitwide", 512)])
+@pytest.mark.parametrize("which,P", [("fit141", 256), ("fit201", 256), ("fit241", 512), ("fit255", 512), ("fit511", 1024), ("fitwide", 512)])
 def test_tables_and_kernel_algorithm_on_cpu(which, P, request):
     """The packed tables + the kernel's sequence of operations (numpy model) reproduce the oracle's filtered row."""
     from joxsz_b200.packer import PackedSetup
@@ -80,7 +87,7 @@ def test_tables_and_kernel_algorithm_on_cpu(which, P, request):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which,nw", [("fit141", 48), ("fit201", 48), ("fit255", 48), ("fit511", 16), ("fitwide", 32)])
+@pytest.mark.parametrize("which,nw", [("fit141", 48), ("fit201", 48), ("fit241", 48), ("fit255", 48), ("fit511", 16), ("fitwide", 32)])
 def test_large_map_loglike_matches_oracle(which, nw, request):
     from joxsz_b200.batched import BatchedLikelihood
     fit = request.getfixturevalue(which)
