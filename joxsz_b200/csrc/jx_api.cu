@@ -291,6 +291,29 @@ extern "C" int jx_create(const jx_setup* s, jx_handle** out) {
         d.nsynth = (int)t.size();
         rc = upload(h, &d.synth, t.data(), t.size());
     }
+    d.synth_tiles = nullptr; d.nsynth_tiles = 0;
+    if (!rc && s->npad > 256) {   // the same pixels in 32 x 32 tiles (u block <= v block; diagonal tiles whole): the large-map
+                                  // kernel stores a tile by rows and its mirror image through a shared-memory transpose
+        std::vector<jx_synth_px> t;
+        const int nt = (H + 31) / 32;
+        for (int ub = 0; ub < nt; ++ub)
+            for (int vb = ub; vb < nt; ++vb)
+                for (int i = 0; i < 32; ++i)
+                    for (int j = 0; j < 32; ++j) {
+                        const int u = 32 * ub + i, v = 32 * vb + j;
+                        jx_synth_px e;
+                        if (u < H && v < H) {
+                            e.dx = s->dx[(size_t)u * H + v];
+                            e.seg = (uint16_t)s->seg[(size_t)u * H + v];
+                            e.u = (uint16_t)u; e.v = (uint16_t)v; e.pad = 0;
+                        } else {
+                            e.dx = 0.0; e.seg = 0; e.u = 0xffff; e.v = 0; e.pad = 0;
+                        }
+                        t.push_back(e);
+                    }
+        d.nsynth_tiles = (int)(t.size() / 1024);
+        rc = upload(h, &d.synth_tiles, t.data(), t.size());
+    }
     if (!rc) {   // beam spectrum per column pair in the register order of the nine-thread column FFT:
                  // [cp][p][t] = bhat[fold(t + 16 rev16(p)), 2cp..2cp+1], t = 0..8
         const int ncp = (Q + 1) / 2, P = s->npad;

@@ -66,6 +66,8 @@ struct jx_dev {
     const double* costab;    // [nmap] cos(2 pi m / nmap)
     const jx_synth_px* synth; // [nsynth] quarter-plane pixels with u <= v, padded with u = 0xffff sentinels
     int nsynth;               // multiple of 256
+    const jx_synth_px* synth_tiles;  // large maps only: the whole quarter plane in 32 x 32 tiles (ub <= vb, row-major), padded with sentinels
+    int nsynth_tiles;                // number of tiles (1024 entries each)
     const double2* bhat_sw;  // [ceil(nq/2)][16][9] beam spectrum of column pair cp in FFT thread order (K3 phase B: position p, thread t = 0..8)
     const double* w_t0;      // [nt]
     int nconv;

@@ -24,12 +24,15 @@
 //     tile it cost a tile's work for one active lane.
 //   * at P = 1024 the s = 3 branch of the radix-4 decimation is never computed: its spectrum samples are the mirror
 //     images X[P - K] of the s = 1 branch (every sequence of the stage is even) (-25 % of the transform work);
+//   * The synthesis walks the quarter plane in 32 x 32 tiles (u block <= v block): a warp evaluates rows of a tile and
+//     stores them as 256-byte runs, the mirror image goes through a shared-memory transpose and leaves as 256-byte
+//     runs too (storing z to [v][u] directly put every lane of a store on its own sector); the next tile's table
+//     entries are in flight meanwhile.
 //   * the spline coefficients of the next walker arrive by TMA bulk copy while the current walker's transforms and
-//     convolution run (they are only read by the synthesis); the synthesis keeps the next batch of table entries in
-//     flight.
+//     convolution run (they are only read by the synthesis).
 // Phase clocks per walker on B200 (scripts/k3_phase_clocks.py, JX_CLK_WORKLOAD=synth255 / synth511), first version ->
-// now: 255 pixels A0 13.8 k, A1 48.7 k, B 73.9 k, C 46.4 k = 183 k -> 14.7 / 34.3 / 62.4 / 32.0 = 143 k cycles;
-// 511 pixels 66 / 391 / 315 / 311 = 1 083 k -> 63-80 / 194-213 / 243-252 / 183-204 = 693-739 k.
+// now: 255 pixels A0 13.8 k, A1 48.7 k, B 73.9 k, C 46.4 k = 183 k -> 11.7 / 33-34 / 62-67 / 32-37 = 143-148 k cycles;
+// 511 pixels 66 / 391 / 315 / 311 = 1 083 k -> 43 / 194-213 / 228-252 / 183-204 = 692-739 k (box to box).
 #include "k3_common.cuh"
 
 #ifdef JX_K3_CLOCKS
@@ -247,31 +250,52 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
         K3M_CLK_DECL;
         mbar_wait(mbar, (uint32_t)(it & 1));
         if (!skip) {
-            // ---- A0: synthesise the quarter-plane map (u <= v listed, mirrored on store)
-            const int4* tab = reinterpret_cast<const int4*>(d.synth);
-            auto tab_load = [&](int base, int4 (&e)[8]) {
+            // ---- A0: synthesise the quarter-plane map, 32 x 32 tiles with u block <= v block.  A warp evaluates rows of
+            // the tile and stores them as 256-byte runs; the mirror image goes through a shared-memory transpose and
+            // leaves as 256-byte runs too (storing z to [v][u] straight away put every lane of a store on its own
+            // sector: the synthesis of a 511-pixel map took 63-80 k cycles, 9-11 % of the kernel)
+            const int4* tab = reinterpret_cast<const int4*>(d.synth_tiles);
+            double* tt_all = reinterpret_cast<double*>(k3m_raw + L.xbuf);      // two [32][33] transpose tiles in the arena
+            const int nt = (H + 31) >> 5, nwarp = NT >> 5;
+            constexpr int RPW = (32 + (NT >> 5) - 1) / (NT >> 5);              // tile rows per warp
+            int4 e[RPW], en[RPW];
+            auto tile_load = [&](int tile, int4 (&x)[RPW]) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int i = base + k * NT + tid;
-                    e[k] = i < d.nsynth ? __ldg(tab + i) : make_int4(0, 0, 0xffff0000, 0);
+                for (int q = 0; q < RPW; ++q) {
+                    const int i = warp + q * nwarp;
+                    x[q] = i < 32 && tile < d.nsynth_tiles ? __ldg(tab + (size_t)tile * 1024 + i * 32 + lane)
+                                                          : make_int4(0, 0, 0xffff0000, 0);
                 }
             };
-            int4 e[8], en[8];
-            tab_load(0, e);
-            for (int base = 0; base < d.nsynth; base += 8 * NT) {
-                if (base + 8 * NT < d.nsynth) tab_load(base + 8 * NT, en);       // the next batch is in flight
+            tile_load(0, e);
+            int tile = 0;
+            for (int ub = 0; ub < nt; ++ub)
+                for (int vb = ub; vb < nt; ++vb, ++tile) {
+                    tile_load(tile + 1, en);                                   // the next tile's entries are in flight
+                    double* tt = tt_all + (tile & 1) * (32 * 33);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int sg = e[k].z & 0xffff, u = (e[k].z >> 16) & 0xffff, v = e[k].w & 0xffff;
-                    if (u != 0xffff) {
-                        const double z = spline_eval(coef_s, d.nseg, sg, __hiloint2double(e[k].y, e[k].x));
-                        __stcg(xs + (size_t)u * pitch + v, z);
-                        __stcg(xs + (size_t)v * pitch + u, z);
+                    for (int q = 0; q < RPW; ++q) {
+                        const int i = warp + q * nwarp;
+                        const int sg = e[q].z & 0xffff, u = (e[q].z >> 16) & 0xffff, v = e[q].w & 0xffff;
+                        double z = 0.0;
+                        if (u != 0xffff) {
+                            z = spline_eval(coef_s, d.nseg, sg, __hiloint2double(e[q].y, e[q].x));
+                            __stcg(xs + (size_t)u * pitch + v, z);
+                        }
+                        if (i < 32) tt[i * 33 + lane] = z;
                     }
-                }
+                    __syncthreads();         // also orders this tile's reads of `tt` before the writes two tiles on
+                    if (ub != vb) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) e[k] = en[k];
-            }
+                        for (int q = 0; q < RPW; ++q) {
+                            const int i = warp + q * nwarp;                    // row of the mirrored tile
+                            const int u = 32 * vb + i, v = 32 * ub + lane;
+                            if (i < 32 && u < H && v < H) __stcg(xs + (size_t)u * pitch + v, tt[lane * 33 + i]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < RPW; ++q) e[q] = en[q];
+                }
         }
         __syncthreads();                       // the coefficients have been read (or are not needed): refill them
         {
