@@ -57,6 +57,13 @@ constexpr int K3M_NT_A = 512, K3M_NT_B = 384, K3M_NT_C = 256;       // threads p
 #define K3M_UB_N 16
 #endif
 constexpr int K3M_NB = JX_BMIX_ROWS, K3M_UB = K3M_UB_N;      // taps, rows per convolution task
+#ifndef K3M_GATHER_N
+#define K3M_GATHER_N 32
+#endif
+// samples per gather chunk of a row transform (x 2 rows = loads in flight per thread; all of a chunk are issued, then
+// all are consumed, so they share scoreboards without harm).  Cycles per walker in A1 at 255 / 511 pixels: 8 samples
+// 32.8 k / 206 k, 16 samples 30.4 k / 192 k, 32 samples 28.9 k / 182 k
+constexpr int K3M_GATHER = K3M_GATHER_N;
 constexpr int K3M_TILES = 4;                                 // tile buffers of the y convolution, at most
 
 // a convolution tile of 32 columns: the 27 mirrored rows -27 .. -1 (copies of rows 27 .. 1), the H rows of the map, 27
@@ -118,7 +125,7 @@ JX_D void k3m_group_fft_even(int t, unsigned gmask, LD&& ld, STV&& stv, ST1&& st
     double re[NS][16], im[NS][16];
     // the gather runs in chunks of G samples: all loads of a chunk are in flight together (L2 latency), and the
     // compiler barrier between chunks keeps it from hoisting every load of the line
-    constexpr int G = 8 / R;
+    constexpr int G = K3M_GATHER / R;
 #pragma unroll
     for (int j0 = 0; j0 < 16; j0 += G) {
         double2 v[G][R];
