@@ -4,7 +4,9 @@
 // equal within rounding at P = 1024 (a quarter of the spectrum samples is taken from its mirror image).  The map of a
 // walker (128 x 257 or 256 x 513 doubles) does not fit the shared memory of an SM, so the phases go out of place
 // between two per-CTA scratch maps that are reused walker after walker and stay in the 126 MB L2 at 255 pixels
-// (A1 xs -> xc, B xc -> xs, C xs -> packed triangle); one CTA of 256 threads per SM at 255 registers.
+// (A1 xs -> xc, B xc -> xc IN PLACE -- a tile is whole in shared memory before its columns are overwritten, and tiles
+// are disjoint column blocks --, C xc -> packed triangle: xs only ever holds the H x H synthesised map, which keeps the
+// working set of a CTA at 1.5 instead of 2.1 MB at 511 pixels); one CTA of 256 threads per SM at 255 registers.
 //   * A row transform (16-thread group, radix-R decimation in frequency around the register FFT-256) gathers its line
 //     ONCE for all branches -- it used to be re-read from L2 per branch, 16 / G dependent chunks of loads each -- and
 //     keeps the 32 NS branch inputs in registers, hence the 255-register budget (256 threads: cycles per walker
@@ -229,8 +231,8 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
     double2* xbuf = xbuf_all + (size_t)grp * JX_XB_ELEMS;
     const uint32_t coef_bytes = (uint32_t)(d.ncoef * sizeof(double));
     const int pitch = d.xs_pitch;
-    double* xs = a.scratch + (size_t)blockIdx.x * hp8 * pitch;      // synthesised map, then the convolved spectra
-    double* xc = a.scratch2 + (size_t)blockIdx.x * hp8 * pitch;     // row spectra
+    double* xs = a.scratch + (size_t)blockIdx.x * hp8 * pitch;      // synthesised map (H x H)
+    double* xc = a.scratch2 + (size_t)blockIdx.x * hp8 * pitch;     // row spectra, convolved in place
 
     for (int i = tid; i < 256; i += NT) fft256_make_twiddle(i, tw_s[i]);
     for (int i = tid; i < P / 2; i += NT) {          // s m < P / 2 for the branches that are computed: half a turn
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
         __syncthreads();
         K3M_CLK(1);
 
-        // ---- B: 55-tap convolution along y, xc -> xs.  [H rows x 32 columns] tiles of the row spectra stream through a
+        // ---- B: 55-tap convolution along y, xc -> xc in place.  [H rows x 32 columns] tiles of the row spectra stream through a
         // ring of shared-memory buffers (cp.async, 16 bytes per thread and copy: a register prefetch queue is never
         // deeper than the six scoreboards of a warp); lane = column, a warp takes a block of K3M_UB rows of a tile.
         // Rows per block: 16 (K3M_UB).  32-row blocks with two tiles per step (so that every warp still has a block
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
                             const int up = r + dd, ua = up < 0 ? -up : up;
                             acc = fma(nyq_s[H + 1 + (dd < 0 ? -dd : dd)], nyq_s[ua < H ? ua : H], acc);
                         }
-                        __stcg(xs + (size_t)r * pitch + (Q - 1), acc);
+                        __stcg(xc + (size_t)r * pitch + (Q - 1), acc);
                     }
                 }
                 for (int task = warp; task < ts * nrb; task += nw) {
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
                     k3m_yconv(tile, lane, u0, tap, acc);
 #pragma unroll
                     for (int k = 0; k < K3M_UB; ++k)
-                        if (u0 + k < H) __stcg(xs + (size_t)(u0 + k) * pitch + kx, acc[k]);
+                        if (u0 + k < H) __stcg(xc + (size_t)(u0 + k) * pitch + kx, acc[k]);
                 }
             }
             cp_async_wait<0>();
@@ -425,13 +427,13 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
         __syncthreads();
         K3M_CLK(2);
 
-        // ---- C: rows back to pixel space, xs -> packed triangle (and the quarter-plane tap)
+        // ---- C: rows back to pixel space, xc -> packed triangle (and the quarter-plane tap)
         double* cq = a.convq ? a.convq + (size_t)w * H * H : nullptr;
         for (int rp = grp; rp < npair; rp += ngroups) {
             const int u0 = 2 * rp, u1 = u0 + 1;
             const bool has1 = u1 < H;
-            const double* r0 = xs + (size_t)u0 * pitch;
-            const double* r1 = xs + (size_t)(has1 ? u1 : u0) * pitch;
+            const double* r0 = xc + (size_t)u0 * pitch;
+            const double* r1 = xc + (size_t)(has1 ? u1 : u0) * pitch;
             double* tri0 = a.tri + (size_t)w * d.ktri + (u0 * H - ((u0 * (u0 - 1)) >> 1) - u0);   // + v
             double* tri1 = tri0 + (H - u0 - 1);
             k3m_group_fft_even<R>(
@@ -460,7 +462,7 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
                 },
                 tw_s, twp_s, xbuf);
         }
-        __syncthreads();        // every read of xs is done before the next walker's synthesis overwrites it
+        __syncthreads();        // the exchange tiles are free: the next synthesis transposes through the same arena
         K3M_CLK(3);
     }
 }
