@@ -41,7 +41,8 @@ extern "C" int jx_debug_k3w_clocks(unsigned long long* out8) {
 #define K3W_CLK(i)
 #endif
 
-// Developer experiment (scripts/k3_phase_clocks.py with JX_CLK_DEFS): -DJX_K3W_NO_F / -DJX_K3W_NO_M build the kernel
+// Developer experiment (scripts/k3_phase_clocks.py with JX_CLK_DEFS; -DJX_K3W_NO_STG drops the triangle stores of C):
+// -DJX_K3W_NO_F / -DJX_K3W_NO_M build the kernel
 // with one warp group doing no work of its own (it keeps the barrier protocol), to time the other group alone.  The
 // results of such a build are meaningless.
 #ifdef JX_K3W_NO_F
@@ -218,8 +219,12 @@ __global__ void __launch_bounds__(KW_NT, 1) k3w_szmap_kernel(const __grid_consta
                     const int n = t + 16 * rev16(p);
                     const int v = fold256(n);
                     if (on && v < H && !(n > 128 && t_edge)) {
+#ifndef JX_K3W_NO_STG
                         if (v >= u0) tri0[v] = re[p];
                         if (has1 && v >= u1) tri1[v] = im[p];
+#else
+                        if (a.W < 0) { tri0[v] = re[p]; tri1[v] = im[p]; }     // experiment: C without its global stores
+#endif
                         if (tapq) {
                             xs[u0 * KW_XS + v] = re[p];
                             if (has1) xs[u1 * KW_XS + v] = im[p];
