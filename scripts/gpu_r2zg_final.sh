@@ -15,6 +15,3 @@ print("e2e", d["e2e"]["value"], "numpy", d["e2e_numpy"]["value"], "collapsed", d
 for k, v in d["secondary"].items():
     print(k, {kk: v.get(kk) for kk in ("value", "ms_per_step", "parity_max_abs_dll_vs_cpu_sample", "error", "map_kernel")}, v.get("stage_ms_per_launch", {}).get("szmap"))
 PY
-for wl in synth255 synth511; do
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k3l2_szmap -s 2 -c 1 -f -o gpurun_out/r02h_k3l2_${wl}_full python bench.py --workload $wl --walkers 8192 --no-secondary --steps 2 --warmup 1 > gpurun_out/ncu_k3l2_$wl.log 2>&1; echo "ncu $wl rc=$?"
-done
