@@ -15,10 +15,10 @@
 //     X[R k + s]; at R = 4 the s = 3 sample comes from lane 15 - t by one shuffle) and stores them as one 16 R-byte run:
 //     the scattered 8-byte stores at an 8 R-byte stride cost the 1024-point row transforms a fifth of their time.
 //   * The y convolution works on [H rows x 32 columns] tiles of the row spectra that all threads stream into a ring of
-//     up to four shared-memory buffers with cp.async (16 bytes per thread and copy; each buffer also receives the 28
-//     tap rows of its columns and keeps a row of zeros that stands for every row beyond the map, so the inner loop
-//     has no predicate), one __syncthreads per tile; a warp convolves 16-row blocks from shared memory as the
-//     256-point kernels do.  Loads straight from L2 into a register queue were bound by the six scoreboards of a warp
+//     up to four shared-memory buffers with cp.async (16 bytes per thread and copy; each buffer physically holds the
+//     27 mirrored rows, the map rows, 27 rows of zeros and the 28 tap rows of its columns, so the inner loop is loads
+//     at immediate offsets and DFMA, no index arithmetic), one __syncthreads per tile; a warp convolves 16-row blocks
+//     from shared memory as the 256-point kernels do.  Loads straight from L2 into a register queue were bound by the six scoreboards of a warp
 //     (a queue of 16 was no faster than one of 8).  Measured and NOT kept: the same tiles fetched with one
 //     cp.async.bulk per 256-byte row (4 096 requests per walker at 511 pixels: request-rate bound, B 318 k -> 438 k
 //     cycles), and row pairs of the transforms staged by cp.async.bulk behind the previous FFT (A1 34 k -> 49 k).
@@ -33,8 +33,10 @@
 //   * the spline coefficients of the next walker arrive by TMA bulk copy while the current walker's transforms and
 //     convolution run (they are only read by the synthesis).
 // Phase clocks per walker on B200 (scripts/k3_phase_clocks.py, JX_CLK_WORKLOAD=synth255 / synth511), first version ->
-// now: 255 pixels A0 13.8 k, A1 48.7 k, B 73.9 k, C 46.4 k = 183 k -> 11.7 / 33-34 / 62-67 / 32-37 = 143-148 k cycles;
-// 511 pixels 66 / 391 / 315 / 311 = 1 083 k -> 43 / 194-213 / 228-252 / 183-204 = 692-739 k (box to box).
+// now: 255 pixels A0 13.8 k, A1 48.7 k, B 73.9 k, C 46.4 k = 183 k -> 11.7 / 28.9 / 66.4 / 35.8 = 143 k cycles;
+// 511 pixels 66 / 391 / 315 / 311 = 1 083 k -> 43 / 182 / 243 / 190 = 657 k (a few per cent from box to box).
+// What bounds B now (0.22 DFMA per clock per scheduler) is documented in profiles/r02_results.md and
+// profiles/r02_dfma_latency_yconv_microbench.txt.
 #include "k3_common.cuh"
 
 #ifdef JX_K3_CLOCKS
