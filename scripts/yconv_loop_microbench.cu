@@ -44,6 +44,32 @@ __global__ void __launch_bounds__(NT, 1) k(double* out, const double* in, int it
     const long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
+        if (STORES == 7) {
+            // nine warps: warps 0-7 compute and stage their results in shared memory, warp 8 does all the global traffic
+            // (the tile fetch by cp.async and the flush of the staged results by plain coalesced stores)
+            if (warp == 8) {
+                __syncthreads();               // X: (nothing to do for the memory warp)
+                __syncthreads();               // Y: the staged results are complete
+                double* g = out + (size_t)blockIdx.x * 4096;
+                const double* st = tile + ROWS * 32;
+#pragma unroll 8
+                for (int q = 0; q < 128; ++q) g[q * 32 + lane] = st[q * 32 + lane];
+#pragma unroll
+                for (int q = 0; q < 96; ++q)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(
+                                     tile + ROWS * 32 + 4096 + 2 * (q * 32 + lane))), "l"(in + 2 * ((q * 32 + lane) % 2048)) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                double acc[UB];
+                yconv<FROM_SMEM>(tile, lane, 16 * warp, tap, acc, sum);
+                __syncthreads();               // X: the memory warp has flushed the previous round
+#pragma unroll
+                for (int kk = 0; kk < UB; ++kk) tile[ROWS * 32 + (16 * warp + kk) * 32 + lane] = acc[kk];
+                __syncthreads();               // Y
+            }
+            continue;
+        }
         if (SKEW == -1) {              // the kernel's tile fetch: global -> shared copies by the computing warps themselves
 #pragma unroll
             for (int q = 0; q < 12; ++q)
@@ -104,14 +130,14 @@ __global__ void __launch_bounds__(NT, 1) k(double* out, const double* in, int it
 template <int A, int B, int C, int D, int NT = 256>
 void run(const char* name, double* out, double* in, long long* cyc) {
     const int iters = 400;
-    const size_t smem = (ROWS * 32 + UB * NT + 24 * NT) * sizeof(double);
+    const size_t smem = (ROWS * 32 + UB * NT + 24 * NT + 8192) * sizeof(double);
     cudaFuncSetAttribute(k<A, B, C, D, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<A, B, C, D, NT><<<148, NT, smem>>>(out, in, iters, cyc);
     k<A, B, C, D, NT><<<148, NT, smem>>>(out, in, iters, cyc);
     cudaDeviceSynchronize();
     long long h; cudaMemcpy(&h, cyc, sizeof h, cudaMemcpyDeviceToHost);
     const double dfma = (double)iters * UB * (2 * NB - 1);
-    printf("%-58s cycles per task %7.0f   DFMA / clk / scheduler %.3f  (%s)\n", name, (double)h / iters, (NT / 128.0) * dfma / (double)h,
+    printf("%-58s cycles per task %7.0f   DFMA / clk / scheduler %.3f  (%s)\n", name, (double)h / iters, ((NT == 288 ? 256 : NT) / 128.0) * dfma / (double)h,
            cudaGetErrorString(cudaGetLastError()));
 }
 
@@ -129,6 +155,7 @@ int main() {
     run<0, 1, 0, 0>("register x, stores, no barrier", out, in, cyc);
     run<2, 1, 1, 0>("smem x preloaded (source order), stores, barrier per task", out, in, cyc);
     run<3, 1, 1, 0>("smem x preloaded + compiler barrier, stores, barrier per task", out, in, cyc);
+    run<1, 7, 0, 0, 288>("nine warps: eight compute + stage, one memory warp (flush by plain stores + cp.async fetch)", out, in, cyc);
     run<1, 3, 1, -1>("smem x, shared-memory stores, barrier per task, + 12 cp.async per thread and task", out, in, cyc);
     run<1, 3, 1, 0>("smem x, shared-memory stores, barrier per task (again)", out, in, cyc);
     run<1, 6, 0, -1>("smem x, staged + bulk store, + 12 cp.async per thread and task", out, in, cyc);
