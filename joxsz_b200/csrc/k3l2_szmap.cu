@@ -54,6 +54,19 @@ extern "C" int jx_debug_k3l2_clocks(unsigned long long* out8) {
 #define K3M_CLK(i)
 #endif
 
+// Timing experiments of phase B (scripts/k3_phase_clocks.py with JX_CLK_DEFS; results of such builds are wrong):
+// -DK3M_NO_STG drops the result stores, -DK3M_NO_FETCH the tile fetches after the first ring fill.
+#ifdef K3M_NO_STG
+#define K3M_EXP_STORE(c) ((c) && a.W < 0)
+#else
+#define K3M_EXP_STORE(c) (c)
+#endif
+#ifdef K3M_NO_FETCH
+#define K3M_EXP_FETCH(c) ((c) && a.W < 0)
+#else
+#define K3M_EXP_FETCH(c) (c)
+#endif
+
 namespace {
 
 constexpr int K3M_NT_A = 512, K3M_NT_B = 384, K3M_NT_C = 256;       // threads per CTA (one CTA per SM): 16 warps at 128 registers, or 12 at 168
@@ -394,7 +407,7 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
                 // fetch refills
                 if (nslot >= 4) cp_async_wait<2>(); else if (nslot == 3) cp_async_wait<1>(); else cp_async_wait<0>();
                 __syncthreads();
-                if (st + nslot - 1 < nstep) step_fetch(st + nslot - 1);
+                if (K3M_EXP_FETCH(st + nslot - 1 < nstep)) step_fetch(st + nslot - 1);
                 cp_async_commit();
                 if (st == 0) {
                     // Nyquist column: one output row per lane (rows dealt over the warps), inputs and taps in the
@@ -421,7 +434,7 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
                     k3m_yconv(tile, lane, u0, tap, acc);
 #pragma unroll
                     for (int k = 0; k < K3M_UB; ++k)
-                        if (u0 + k < H) __stcg(xc + (size_t)(u0 + k) * pitch + kx, acc[k]);
+                        if (K3M_EXP_STORE(u0 + k < H)) __stcg(xc + (size_t)(u0 + k) * pitch + kx, acc[k]);
                 }
             }
             cp_async_wait<0>();
