@@ -81,6 +81,12 @@ constexpr int K3M_NB = JX_BMIX_ROWS, K3M_UB = K3M_UB_N;      // taps, rows per c
 // all are consumed, so they share scoreboards without harm).  Cycles per walker in A1 at 255 / 511 pixels: 8 samples
 // 32.8 k / 206 k, 16 samples 30.4 k / 192 k, 32 samples 28.9 k / 182 k
 constexpr int K3M_GATHER = K3M_GATHER_N;
+#ifndef K3M_TS_MIN_N
+#define K3M_TS_MIN_N 2
+#endif
+// tiles per step (= per block barrier) of the y convolution, at least, when the ring holds two such steps: at 255 pixels
+// two tiles per step, i.e. two blocks per warp between barriers: B 64.8 k -> 63.1 k cycles per walker
+constexpr int K3M_TS_MIN = K3M_TS_MIN_N;
 constexpr int K3M_TILES = 4;                                 // tile buffers of the y convolution, at most
 
 // a convolution tile of 32 columns: the 27 mirrored rows -27 .. -1 (copies of rows 27 .. 1), the H rows of the map, 27
@@ -368,6 +374,7 @@ __global__ void __launch_bounds__(K3M_NT, 1) k3l2_szmap_kernel(const __grid_cons
             const int ncw = (Q - 1) >> 5, nrb = (H + K3M_UB - 1) / K3M_UB, nw = NT >> 5;
             const int ntb = L.ntile, tile_elems = k3m_tile_rows(H) * 32;
             int ts = nrb < nw ? nw / nrb : 1;                    // tiles per step
+            if (ts < K3M_TS_MIN) ts = K3M_TS_MIN;
             if (ntb / ts < 2) ts = 1;
             const int nslot = ntb / ts, nstep = (ncw + ts - 1) / ts;      // ring slots of ts tiles each; steps
             double* tiles = reinterpret_cast<double*>(k3m_raw + L.xbuf);
